@@ -1,0 +1,192 @@
+// K1/K2 of SURVEY.md section 2.3: embedding gather, (skip-)RMSNorm + per-token int8 quantisation,
+// per-token int8 quantisation of plain rows.  HBM-bound row kernels: one CTA per row, 128-bit
+// loads, warp-shuffle + shared-memory reductions, the row stays in L1 between passes.
+//
+// Numeric contract (oracle/llama_ref.py: rmsnorm_f32, quant_rows):
+//   var = mean(x^2) fp32;  inv = 1 / sqrt(var + eps);  y = (x * inv) * gamma;
+//   amax = max|y|;  scale = amax / 127;  q = clamp(rint(y * (127 / amax)), -127, 127).
+#include "common.cuh"
+
+namespace b2llm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct alignas(16) Half8 {
+    __half2 v[4];
+};
+
+__device__ __forceinline__ Half8 ld8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
+__device__ __forceinline__ void st8(__half* p, const Half8& v) { *reinterpret_cast<Half8*>(p) = v; }
+
+__device__ __forceinline__ int q8(float y, float inv_scale) {
+    int q = __float2int_rn(__fmul_rn(y, inv_scale));
+    return max(-127, min(127, q));
+}
+
+// x: [rows, hidden] fp16 (updated in place when skip != nullptr)
+__global__ void __launch_bounds__(kThreads) rmsnorm_quant_kernel(__half* __restrict__ x, const __half* __restrict__ skip,
+                                                                const __half* __restrict__ gamma, float eps, int hidden,
+                                                                int8_t* __restrict__ q, float* __restrict__ scale,
+                                                                __half* __restrict__ y_out) {
+    __shared__ float scratch[32];
+    const int64_t row = blockIdx.x;
+    __half* xr = x + row * hidden;
+    const int nvec = hidden >> 3;
+
+    // pass 1: residual join (optional) + sum of squares
+    float ss = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += kThreads) {
+        Half8 a = ld8(xr + v * 8);
+        if (skip != nullptr) {
+            const Half8 b = ld8(skip + row * hidden + v * 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
+                a.v[i] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+            }
+            st8(xr + v * 8, a);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(a.v[i]);
+            ss += f.x * f.x + f.y * f.y;
+        }
+    }
+    ss = block_sum(ss, scratch);
+    const float var = ss / (float)hidden;
+    const float inv = __fdiv_rn(1.0f, sqrtf(__fadd_rn(var, eps)));
+
+    if (q == nullptr) {  // plain fp16 output
+        for (int v = threadIdx.x; v < nvec; v += kThreads) {
+            const Half8 a = ld8(xr + v * 8), g = ld8(gamma + v * 8);
+            Half8 o;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = __half22float2(a.v[i]), fg = __half22float2(g.v[i]);
+                o.v[i] = __floats2half2_rn(__fmul_rn(__fmul_rn(fa.x, inv), fg.x), __fmul_rn(__fmul_rn(fa.y, inv), fg.y));
+            }
+            st8(y_out + row * hidden + v * 8, o);
+        }
+        return;
+    }
+
+    // pass 2: row max of |y|
+    float amax = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += kThreads) {
+        const Half8 a = ld8(xr + v * 8), g = ld8(gamma + v * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = __half22float2(a.v[i]), fg = __half22float2(g.v[i]);
+            amax = fmaxf(amax, fabsf(__fmul_rn(__fmul_rn(fa.x, inv), fg.x)));
+            amax = fmaxf(amax, fabsf(__fmul_rn(__fmul_rn(fa.y, inv), fg.y)));
+        }
+    }
+    amax = block_max(amax, scratch);
+    const float inv_scale = amax > 0.f ? __fdiv_rn(127.0f, amax) : 0.f;
+    if (threadIdx.x == 0) scale[row] = __fdiv_rn(amax, 127.0f);
+
+    // pass 3: quantise, 8 bytes per store
+    for (int v = threadIdx.x; v < nvec; v += kThreads) {
+        const Half8 a = ld8(xr + v * 8), g = ld8(gamma + v * 8);
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = __half22float2(a.v[i]), fg = __half22float2(g.v[i]);
+            const int q0 = q8(__fmul_rn(__fmul_rn(fa.x, inv), fg.x), inv_scale);
+            const int q1 = q8(__fmul_rn(__fmul_rn(fa.y, inv), fg.y), inv_scale);
+            w[i >> 1] |= (uint32_t)(q0 & 0xff) << (16 * (i & 1));
+            w[i >> 1] |= (uint32_t)(q1 & 0xff) << (16 * (i & 1) + 8);
+        }
+        *reinterpret_cast<uint2*>(q + row * hidden + v * 8) = make_uint2(w[0], w[1]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) quant_rows_kernel(const __half* __restrict__ x, int cols,
+                                                             int8_t* __restrict__ q, float* __restrict__ scale) {
+    __shared__ float scratch[32];
+    const int64_t row = blockIdx.x;
+    const __half* xr = x + row * cols;
+    const int nvec = cols >> 3;
+    float amax = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += kThreads) {
+        const Half8 a = ld8(xr + v * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(a.v[i]);
+            amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+        }
+    }
+    amax = block_max(amax, scratch);
+    const float inv_scale = amax > 0.f ? __fdiv_rn(127.0f, amax) : 0.f;
+    if (threadIdx.x == 0) scale[row] = __fdiv_rn(amax, 127.0f);
+    for (int v = threadIdx.x; v < nvec; v += kThreads) {
+        const Half8 a = ld8(xr + v * 8);
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(a.v[i]);
+            w[i >> 1] |= (uint32_t)(q8(f.x, inv_scale) & 0xff) << (16 * (i & 1));
+            w[i >> 1] |= (uint32_t)(q8(f.y, inv_scale) & 0xff) << (16 * (i & 1) + 8);
+        }
+        *reinterpret_cast<uint2*>(q + row * cols + v * 8) = make_uint2(w[0], w[1]);
+    }
+}
+
+// out[i, :] = table[ids[i], :]
+__global__ void embedding_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ table, int hidden, int vocab,
+                                 __half* __restrict__ out) {
+    const int64_t i = blockIdx.x;
+    int64_t id = ids[i];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const int nvec = hidden >> 3;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + i * hidden + v * 8, ld8(table + id * hidden + v * 8));
+}
+
+// out[b, :] = x[seq_starts[b + 1] - 1, :]   (last token of every sequence)
+__global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* __restrict__ seq_starts, int hidden,
+                                   __half* __restrict__ out) {
+    const int64_t b = blockIdx.x;
+    const int64_t t = seq_starts[b + 1] - 1;
+    const int nvec = hidden >> 3;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + b * hidden + v * 8, ld8(x + t * hidden + v * 8));
+}
+
+}  // namespace
+
+int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, const __half* gamma, float eps, int64_t rows,
+                             int hidden, int8_t* q, float* scale, __half* y) {
+    B2_REQUIRE(hidden % 8 == 0, B2LLM_ERR_INVALID_VALUE, "rmsnorm: hidden must be a multiple of 8");
+    B2_REQUIRE((q != nullptr && scale != nullptr) || y != nullptr, B2LLM_ERR_INVALID_VALUE, "rmsnorm: no output");
+    if (rows == 0) return B2LLM_OK;
+    rmsnorm_quant_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, skip, gamma, eps, hidden, q, scale, y);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_quant_rows(cudaStream_t s, const __half* x, int64_t rows, int cols, int8_t* q, float* scale) {
+    B2_REQUIRE(cols % 8 == 0, B2LLM_ERR_INVALID_VALUE, "quant_rows: cols must be a multiple of 8");
+    if (rows == 0) return B2LLM_OK;
+    quant_rows_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, cols, q, scale);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_embedding(cudaStream_t s, const int64_t* ids, const __half* table, int64_t n, int hidden, int vocab,
+                         __half* out) {
+    if (n == 0) return B2LLM_OK;
+    embedding_kernel<<<(unsigned)n, 128, 0, s>>>(ids, table, hidden, vocab, out);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_gather_rows(cudaStream_t s, const __half* x, const int64_t* seq_starts, int64_t batch, int hidden,
+                           __half* out) {
+    if (batch == 0) return B2LLM_OK;
+    gather_rows_kernel<<<(unsigned)batch, 128, 0, s>>>(x, seq_starts, hidden, out);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+}  // namespace b2llm
