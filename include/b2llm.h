@@ -162,6 +162,13 @@ B2LLM_API int32_t b2llm_engine_staged_inputs(b2llm_engine* e, const int64_t** to
                                              const int64_t** start_pos);
 /* number of kernels the last forward launched (bench.py's gpu_launches) */
 B2LLM_API int64_t b2llm_engine_last_launch_count(const b2llm_engine* e);
+/* per-kernel-class device timing with CUDA events on the engine stream (bench.py's roofline leg).
+ * classes: 0 attention (decode attention kernel [+ split merge, + prefill attention]), 1 the layer
+ * GEMMs, 2 lm_head.  profile(e, 1) starts recording; profile_read sums the spans recorded since,
+ * synchronises the stream, and resets. */
+B2LLM_API int32_t b2llm_engine_profile(b2llm_engine* e, int32_t enable);
+B2LLM_API int32_t b2llm_engine_profile_read(b2llm_engine* e, double* ms_by_class, int64_t* count_by_class,
+                                            int32_t num_classes);
 /* debugging / parity: copy an intermediate of the last forward to the host.
  * what: 0 residual stream fp16 [num_tokens, hidden] after the last layer; 1 qkv fp16 (last layer, after
  * rope); 2 attention output fp16 (last layer); 3 logits fp32 [batch, vocab] */

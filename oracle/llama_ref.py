@@ -25,7 +25,8 @@ Numeric conventions (the CUDA kernels implement the same cast points; DESIGN.md 
   residual stream and all inter-op activations are fp16; every reduction and every epilogue
   is fp32; int8 rounding is round-half-to-even, clamp [-127, 127]; activation scale =
   rowmax/127 (fp32); KV scale = fp16(groupmax/127); decode attention reads the *quantised*
-  cache for every position including the current token; prefill attention uses the fresh
+  cache for every position including the current token, dequantised values being fp16
+  (fp16(int8 * scale), the tensor-core operand type); prefill attention uses the fresh
   fp16 K/V for the new tokens (and the dequantised cache for a cached prefix).
 """
 from __future__ import annotations
@@ -58,9 +59,17 @@ def quant_rows(y: np.ndarray):
     return q, scale
 
 
-def gemm_i8_acc(a8: np.ndarray, w8: np.ndarray) -> np.ndarray:
+def gemm_i8_acc_numpy(a8: np.ndarray, w8: np.ndarray) -> np.ndarray:
     """exact int32 accumulation of int8 [M,K] x int8 [N,K]^T (float64 BLAS is exact: |acc| < 2^53)."""
     return (a8.astype(np.float64) @ w8.astype(np.float64).T).astype(np.int64).astype(np.int32)
+
+
+def gemm_i8_acc(a8: np.ndarray, w8: np.ndarray) -> np.ndarray:
+    """same result through the C restatement (oracle/csrc/oracle_kernels.c) when it is available --
+    integer arithmetic, so the two are identical bit for bit (tests/test_oracle_cpu.py checks)."""
+    from . import _native
+    out = _native.gemm_i8_i32(a8, w8)
+    return out if out is not None else gemm_i8_acc_numpy(a8, w8)
 
 
 def dequant_acc(acc: np.ndarray, a_scale: np.ndarray, w_scale: np.ndarray) -> np.ndarray:
@@ -115,9 +124,10 @@ def kv_quant(x16: np.ndarray, group: int = 8):
 
 
 def kv_dequant(q8: np.ndarray, s16: np.ndarray, group: int = 8) -> np.ndarray:
+    """dequantised cache values are fp16 (the tensor-core operand type): fp16(int8 * scale), as fp32."""
     shp = q8.shape
     x = q8.astype(F32).reshape(shp[:-1] + (shp[-1] // group, group))
-    return (x * s16.astype(F32)[..., None]).reshape(shp)
+    return (x * s16.astype(F32)[..., None]).astype(np.float16).astype(F32).reshape(shp)
 
 
 # --------------------------------------------------------------------------- KV cache
@@ -245,8 +255,13 @@ class LlamaOracle:
             return dequant_acc(acc, s, lw[name + "_s"])
         return gemm_f16_acc(x_f32_or_16.astype(np.float16), lw[name])
 
-    def forward(self, step: Step, trace: dict | None = None) -> np.ndarray:
-        """returns fp32 logits [B, vocab] (row b = last token of sequence b)."""
+    def forward(self, step: Step, trace: dict | None = None, ulp_nudge: bool = False) -> np.ndarray:
+        """returns fp32 logits [B, vocab] (row b = last token of sequence b).
+
+        ``ulp_nudge``: move the largest-magnitude element of every attention-output row by one fp16
+        ulp before it is re-quantised.  Used by the tests to measure how far the logits of this
+        algorithm move under the smallest representable perturbation (the noise floor any two
+        implementations with different fp32 summation orders are subject to)."""
         d = self.desc
         D, Hq, Hkv = d.head_dim, d.num_heads, d.num_kv_heads
         T = len(step.token_inputs)
@@ -300,6 +315,10 @@ class LlamaOracle:
                         Vf = np.concatenate([kv_dequant(pv8, pvs, d.cache_quant_group), Vf])
                     attn[t0:t1] = _attend(q[t0:t1].astype(F32), Kf, Vf, sp + np.arange(n))
             attn16 = attn.reshape(T, Hq * D).astype(np.float16)
+            if ulp_nudge:
+                j = np.abs(attn16.astype(F32)).argmax(axis=1)
+                r = np.arange(T)
+                attn16[r, j] = np.nextafter(attn16[r, j], np.float16(0))
             if trace is not None and l == 0:
                 trace["l0_attn"] = attn16.copy()
             o = self._linear(attn16.astype(F32) if d.quant_method == 1 else attn16, lw, "wo")

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(128) attn_simple_kernel(AttnParams p) {
             const float vs = __half2float(p.scale[(p.cs.kv + off) / p.group + g]);
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
-                kx[i] = (float)kr[lane * PER + i] * ks;
-                vx[i] = (float)vr[lane * PER + i] * vs;
+                kx[i] = __half2float(__float2half_rn(__fmul_rn((float)kr[lane * PER + i], ks)));
+                vx[i] = __half2float(__float2half_rn(__fmul_rn((float)vr[lane * PER + i], vs)));
             }
         } else {
             const int64_t tj = p.seq_starts[b] + (j - sp);
@@ -298,8 +298,13 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_decode_mma_kernel(AttnPara
             o[j][0] *= corr;
             o[j][1] *= corr;
         }
+        // P enters the tensor core as hi + lo fp16 halves (~22 significant bits), so the only fp16
+        // roundings on this path are the dequantised K / V values, which the oracle reproduces
         __half2 p01 = __floats2half2_rn(pv[0], pv[1]), p23 = __floats2half2_rn(pv[2], pv[3]);
+        const float2 f01 = __half22float2(p01), f23 = __half22float2(p23);
+        __half2 q01 = __floats2half2_rn(pv[0] - f01.x, pv[1] - f01.y), q23 = __floats2half2_rn(pv[2] - f23.x, pv[3] - f23.y);
         const uint32_t pa0 = *reinterpret_cast<uint32_t*>(&p01), pa2 = *reinterpret_cast<uint32_t*>(&p23);
+        const uint32_t pl0 = *reinterpret_cast<uint32_t*>(&q01), pl2 = *reinterpret_cast<uint32_t*>(&q23);
 
         // ---- O += P V : lane (g, t) supplies column n = g of every n-tile, i.e. d = 16 g + j, for tokens
         // {2t, 2t+1} (B0) and {8+2t, 9+2t} (B1)
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_decode_mma_kernel(AttnPara
                 const uint32_t b0 = deq2(lop3_and_xor(prmt(wa[w], wb[w], sel), 0x00FF00FFu, 0x64806480u), s_ab);
                 const uint32_t b1 = deq2(lop3_and_xor(prmt(wc[w], wdd[w], sel), 0x00FF00FFu, 0x64806480u), s_cd);
                 mma_f16_16816(o[j], pa0, 0u, pa2, 0u, b0, b1);
+                mma_f16_16816(o[j], pl0, 0u, pl2, 0u, b0, b1);
             }
         }
         st = (st + 1) % NSTAGE;
@@ -441,7 +447,8 @@ AttnParams make_params(const AttnArgs& a) {
 
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
     (void)head_dim;
-    return batch * num_heads * 64 * 130 * (int64_t)sizeof(float);
+    // rows = sequences * q heads * splits; choose_splits keeps sequences * splits <= sequences + 444
+    return (batch + 444) * num_heads * 130 * (int64_t)sizeof(float);
 }
 
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end) {

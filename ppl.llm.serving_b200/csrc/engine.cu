@@ -100,7 +100,39 @@ struct b2llm_engine {
     int64_t last_tokens = 0;
     int64_t last_batch = 0;
     int attn_impl = 0, gemm_impl = 0;
+    // optional per-kernel-class timing with CUDA events on the engine stream (bench.py roofline)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<std::pair<int, std::pair<size_t, size_t>>> ev_spans;  // (class, (begin, end))
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            ev_pool.push_back(ev);
+        }
+        return ev_pool[ev_used++];
+    }
 };
+
+namespace {
+struct Span {  // RAII: records begin / end events around a kernel class when profiling is on
+    b2llm_engine* e;
+    int cls;
+    size_t b = 0;
+    Span(b2llm_engine* e_, int cls_) : e(e_), cls(cls_) {
+        if (!e->profiling) return;
+        b = e->ev_used;
+        cudaEventRecord(e->next_event(), e->stream);
+    }
+    ~Span() {
+        if (!e->profiling) return;
+        const size_t en = e->ev_used;
+        cudaEventRecord(e->next_event(), e->stream);
+        e->ev_spans.push_back({cls, {b, en}});
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -124,6 +156,7 @@ int32_t finalize_linear(b2llm_engine* e, Linear& L, const __half* w16) {
 int32_t gemm(b2llm_engine* e, const void* a, const float* a_scale, const Linear& L, int64_t M, int epi, void* out,
              int64_t ldc) {
     const bool i8 = e->d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
+    Span span(e, 1);
     if (e->gemm_impl != 1 && gemm_tc_available()) {
         const int32_t rc = launch_gemm_tc(e->stream, i8, a, a_scale, L.w.p, L.scale.as<float>(), M, L.N, L.K, epi, out, ldc);
         if (rc != B2LLM_ERR_UNSUPPORTED) return rc;
@@ -278,6 +311,7 @@ extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
                           &L.gate_up.scale, &L.down.w, &L.down.scale, &L.gate_stage, &L.up_stage})
             b->release();
     }
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : {&e->embedding, &e->final_norm, &e->lm_head, &e->rope_cos, &e->rope_sin, &e->x, &e->a8, &e->a_s,
                       &e->qkv, &e->attn, &e->act, &e->b8, &e->b_s, &e->tmp, &e->y16, &e->xl, &e->yl, &e->logits,
                       &e->attn_ws, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
@@ -590,11 +624,14 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
                                         e->rope_sin.as<float>(), (int8_t*)e->kv_cache, (__half*)e->kv_scale)))
             return rc;
         aa.layer = l;
-        if (e->attn_impl == 1 || e->D != 128) {
-            if ((rc = launch_attention_simple(s, aa, 0, T))) return rc;
-        } else {
-            if ((rc = launch_attention_decode_mma(s, aa))) return rc;
-            if ((rc = launch_attention_simple(s, aa, decode_tokens, T))) return rc;
+        {
+            Span span(e, 0);
+            if (e->attn_impl == 1 || e->D != 128) {
+                if ((rc = launch_attention_simple(s, aa, 0, T))) return rc;
+            } else {
+                if ((rc = launch_attention_decode_mma(s, aa))) return rc;
+                if ((rc = launch_attention_simple(s, aa, decode_tokens, T))) return rc;
+            }
         }
         if (i8) {
             if ((rc = launch_quant_rows(s, e->attn.as<__half>(), T, e->nq * e->D, e->a8.as<int8_t>(), e->a_s.as<float>()))) return rc;
@@ -653,6 +690,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
         head.N = d.vocab_size;
         head.K = h;
         int32_t r2 = B2LLM_ERR_UNSUPPORTED;
+        Span span(e, 2);
         if (e->gemm_impl != 1 && gemm_tc_available())
             r2 = launch_gemm_tc(s, false, e->yl.p, nullptr, head.w.p, nullptr, B, head.N, head.K, EPI_F32, e->logits.p, d.vocab_size);
         if (r2 == B2LLM_ERR_UNSUPPORTED)
@@ -663,6 +701,31 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
     e->last_launches = g_launch_count - launches0;
     e->last_tokens = T;
     e->last_batch = B;
+    return B2LLM_OK;
+}
+
+extern "C" int32_t b2llm_engine_profile(b2llm_engine* e, int32_t enable) {
+    B2_REQUIRE(e, B2LLM_ERR_INVALID_VALUE, "null engine");
+    e->profiling = enable != 0;
+    e->ev_used = 0;
+    e->ev_spans.clear();
+    return B2LLM_OK;
+}
+
+extern "C" int32_t b2llm_engine_profile_read(b2llm_engine* e, double* ms_by_class, int64_t* count_by_class,
+                                             int32_t num_classes) {
+    B2_REQUIRE(e && ms_by_class && count_by_class && num_classes > 0, B2LLM_ERR_INVALID_VALUE, "profile_read: bad arguments");
+    B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < num_classes; ++i) { ms_by_class[i] = 0.0; count_by_class[i] = 0; }
+    for (auto& sp : e->ev_spans) {
+        if (sp.first >= num_classes) continue;
+        float ms = 0.f;
+        B2_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev_pool[sp.second.first], e->ev_pool[sp.second.second]));
+        ms_by_class[sp.first] += ms;
+        count_by_class[sp.first] += 1;
+    }
+    e->ev_used = 0;
+    e->ev_spans.clear();
     return B2LLM_OK;
 }
 

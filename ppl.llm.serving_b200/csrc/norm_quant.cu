@@ -20,6 +20,19 @@ struct alignas(16) Half8 {
 __device__ __forceinline__ Half8 ld8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
 __device__ __forceinline__ void st8(__half* p, const Half8& v) { *reinterpret_cast<Half8*>(p) = v; }
 
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = (lane < nw) ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
 __device__ __forceinline__ int q8(float y, float inv_scale) {
     int q = __float2int_rn(__fmul_rn(y, inv_scale));
     return max(-127, min(127, q));
@@ -31,12 +44,15 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_quant_kernel(__half* __restr
                                                                 int8_t* __restrict__ q, float* __restrict__ scale,
                                                                 __half* __restrict__ y_out) {
     __shared__ float scratch[32];
+    __shared__ double dscratch[32];
     const int64_t row = blockIdx.x;
     __half* xr = x + row * hidden;
     const int nvec = hidden >> 3;
 
-    // pass 1: residual join (optional) + sum of squares
-    float ss = 0.f;
+    // pass 1: residual join (optional) + sum of squares.  Accumulated in fp64 so that the variance is
+    // independent of the reduction order (the oracle uses float64 too) and the int8 codes downstream
+    // are reproducible bit for bit.
+    double ss = 0.0;
     for (int v = threadIdx.x; v < nvec; v += kThreads) {
         Half8 a = ld8(xr + v * 8);
         if (skip != nullptr) {
@@ -51,11 +67,11 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_quant_kernel(__half* __restr
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float2 f = __half22float2(a.v[i]);
-            ss += f.x * f.x + f.y * f.y;
+            ss += (double)f.x * (double)f.x + (double)f.y * (double)f.y;
         }
     }
-    ss = block_sum(ss, scratch);
-    const float var = ss / (float)hidden;
+    ss = block_sum_f64(ss, dscratch);
+    const float var = (float)(ss / (double)hidden);
     const float inv = __fdiv_rn(1.0f, sqrtf(__fadd_rn(var, eps)));
 
     if (q == nullptr) {  // plain fp16 output

@@ -28,6 +28,61 @@ INT64_MAX = np.iinfo(np.int64).max
 
 
 @dataclass
+class ModelConfig:
+    """ppl::llm::ModelConfig (src/common/config.h:64-84) + the graph-level constants and quant method
+    the reference keeps elsewhere (resource_manager.cc:49-56; config.h:74)."""
+    hidden_dim: int = 0
+    intermediate_dim: int = 0
+    num_layers: int = 0
+    num_heads: int = 0
+    num_kv_heads: int = 0
+    vocab_size: int = 0
+    norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    cache_quant_bit: int = 8
+    cache_quant_group: int = 8
+    cache_layout: int = 3
+    cache_mode: int = 1
+    page_size: int = 16
+    dynamic_batching: bool = True
+    auto_causal: bool = True
+    quant_method: int = 1       # 0 "none", 1 "online_i8i8"
+    max_position: int = 4096
+
+    @property
+    def head_dim(self):
+        return self.hidden_dim // self.num_heads
+
+
+def ParseModelConfig(model_param_path: str, model_config: ModelConfig) -> bool:
+    """params.json reader with the reference's required keys and defaults (src/common/config.cc:31-148)."""
+    import json
+    try:
+        with open(model_param_path) as f:
+            doc = json.load(f)
+    except (OSError, ValueError):
+        return False
+    required = ["num_heads", "num_layers", "hidden_dim", "intermediate_dim", "vocab_size", "cache_quant_bit",
+                "cache_quant_group", "cache_layout", "cache_mode", "dynamic_batching", "auto_causal"]
+    for k in required:
+        if k not in doc:
+            return False
+    for k in required:
+        setattr(model_config, k, type(getattr(model_config, k))(doc[k]))
+    model_config.num_kv_heads = int(doc.get("num_kv_heads", model_config.num_heads))
+    if model_config.cache_mode == 1:
+        if "page_size" not in doc:
+            return False
+        model_config.page_size = int(doc["page_size"])
+    return True
+
+
+LLAMA2_7B = dict(hidden_dim=4096, intermediate_dim=11008, num_layers=32, num_heads=32, num_kv_heads=32, vocab_size=32000)
+LLAMA2_13B = dict(hidden_dim=5120, intermediate_dim=13824, num_layers=40, num_heads=40, num_kv_heads=40, vocab_size=32000)
+LLAMA2_70B = dict(hidden_dim=8192, intermediate_dim=28672, num_layers=80, num_heads=64, num_kv_heads=8, vocab_size=32000)
+
+
+@dataclass
 class ModelInput:
     """src/engine/llm_engine.h:40-60 (host vectors, rebuilt every step by the generator)."""
     decoding_batches: int = 0

@@ -15,7 +15,24 @@ from oracle import sampler_ref
 from oracle.weights import ModelDesc, synth_tensor, quantize_weight_per_channel
 from ppl_llm_serving_b200 import capi
 from ppl_llm_serving_b200.engine import _ptr
-from helpers import dev, stream_ptr, make_step_c, make_geom, random_pages
+from helpers import dev as _dev, stream_ptr, make_step_c, make_geom, random_pages
+
+_KEEP = []
+
+
+def dev(a):
+    """device copy that stays alive until the test ends (a temporary passed as _ptr(dev(x)) would be
+    freed -- and its block reused by the next allocation -- before the kernel runs)"""
+    t = _dev(a)
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_keep():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 pytestmark = pytest.mark.gpu
 
@@ -302,7 +319,7 @@ def test_attention_decode_mha(lib, impl, layout, mode):
 @pytest.mark.parametrize("impl", [1, 2])
 def test_attention_decode_gqa_and_splits(lib, impl):
     desc = _mk_desc(3, 1, nq=8, nkv=1)  # 8 q heads share one kv head (70B TP=8 shape per rank)
-    _attention_case(lib, desc, [1, 1], [1500, 700], 2, impl, seed=3)  # few CTAs -> split-KV + merge
+    _attention_case(lib, desc, [1, 1], [1500, 700], 2, impl, T_cache=4096, seed=3)  # few CTAs -> split-KV + merge
     desc = _mk_desc(3, 1, nq=8, nkv=2)
     _attention_case(lib, desc, [1] * 3, [40, 1, 257], 3, impl, seed=4)
 
