@@ -1,10 +1,428 @@
-// placeholder until the tcgen05 kernel lands (see gemm_mma.cu for the baseline path)
+// Blackwell-native GEMM for the W8A8 projections (K3/K8/K9/K10) and the fp16 lm_head (K11):
+//   C[M,N] = A[M,K] * W[N,K]^T,  int8 x int8 -> int32 (tcgen05.mma kind::i8, exact) or
+//   fp16 x fp16 -> fp32 (kind::f16), accumulators in TMEM, operands staged by TMA.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 128 B A tile and a BN x 128 B W
+//              tile per stage (128-byte swizzle), mbarrier expect_tx / complete_tx
+//   warp 1     TMEM allocator + MMA issuer: one lane issues 4 x tcgen05.mma (UMMA 128 x BN x 32 B) per
+//              stage, tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld of the accumulator (one TMEM lane = one output row per thread),
+//              fused dequant (a_scale[m] * w_scale[n]) + {fp16 store | residual add | SwiGLU | fp32 store}
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i + 1.  Tiles are walked m-fastest so CTAs running side by side share the weight
+// tile through L2.  Everything is expressed in BYTES of K: int8 k32 and fp16 k16 UMMA steps are both
+// 32 bytes, so one kernel serves both element types.
+//
+// Results are bit-identical to gemm_mma.cu for int8 (integer accumulation, same fp32 epilogue).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
+
 namespace b2llm {
-bool gemm_tc_available() { return false; }
-int32_t launch_gemm_tc(cudaStream_t, bool, const void*, const float*, const void*, const float*, int64_t, int, int, int,
-                       void*, int64_t) {
-    set_last_error("tcgen05 gemm not built");
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKB = 128;          // bytes of K per stage = one 128 B swizzle atom = 4 UMMA k-steps
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;      // warps 2..5 are the epilogue
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int A_BYTES = BM * BKB;            // 16 KB
+    static constexpr int B_BYTES = BN * BKB;            // 32 / 16 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;            // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool I8>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    if constexpr (I8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+            ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+            ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle operand descriptor (sm_100 version 1): 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)0 << 16;                            // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+template <bool I8>
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    uint32_t d = 0;
+    d |= (I8 ? 2u : 1u) << 4;              // accumulator: S32 / F32
+    d |= (I8 ? 1u : 0u) << 7;              // A: signed int8 / fp16
+    d |= (I8 ? 1u : 0u) << 10;             // B
+    // a_major = b_major = 0 (K-major)
+    d |= (uint32_t)(bn >> 3) << 17;        // N
+    d |= (uint32_t)(BM >> 4) << 24;        // M
+    return d;
+}
+
+template <bool I8, int EPI, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const float* __restrict__ a_scale, const float* __restrict__ w_scale, int M, int N, int Kb,
+                   void* __restrict__ out, int64_t ldc) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 1024 B alignment for the swizzle atoms
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int nk = Kb / BKB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // whole warp allocates TMEM
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    tma_load_2d(sa, &map_a, full_bar(stage), kb * BKB, m_blk * BM);
+                    tma_load_2d(sb, &map_w, full_bar(stage), kb * BKB, n_blk * BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<I8>(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BKB / 32; ++k)  // +32 B along K inside the swizzle atom = +2 in the address field
+                        tc_mma<I8>(tmem_c, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));  // accumulator complete
+            }
+        }
+    } else {
+        // epilogue: TMEM lane quarter is fixed by warp id % 4
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int m = m_blk * BM + quarter * 32 + lane;
+            const float sa_m = (I8 && m < M) ? a_scale[m] : 1.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int n0 = n_blk * BN + c * 32;
+                if (n0 >= N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                if (m < M) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if constexpr (I8)
+                            v[i] = dequant((int)r[i], sa_m, __ldg(w_scale + n0 + i));
+                        else
+                            v[i] = __uint_as_float(r[i]);
+                    }
+                    if constexpr (EPI == EPI_F16 || EPI == EPI_RESIDUAL) {
+                        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + n0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk;
+                            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+                            if constexpr (EPI == EPI_RESIDUAL) {
+                                const uint4 old = *reinterpret_cast<const uint4*>(orow + q * 8);
+                                const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ow[j]));
+                                    __half2 h = __floats2half2_rn(__fadd_rn(o2.x, v[q * 8 + 2 * j]), __fadd_rn(o2.y, v[q * 8 + 2 * j + 1]));
+                                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __half2 h = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+                                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
+                        }
+                    } else if constexpr (EPI == EPI_SWIGLU) {
+                        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + (n0 >> 1);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            uint4 pk;
+                            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = q * 16 + 4 * j;
+                                __half2 h = __floats2half2_rn(silu_mul_f32(v[i], v[i + 1]), silu_mul_f32(v[i + 2], v[i + 3]));
+                                pw[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
+                        }
+                    } else {
+                        float* orow = reinterpret_cast<float*>(out) + (int64_t)m * ldc + n0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(orow + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+std::once_flag g_once;
+
+void init_once() {
+    std::call_once(g_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+        else
+            cudaGetLastError();
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10)
+            g_num_sms = prop.multiProcessorCount;
+        else
+            cudaGetLastError();
+    });
+}
+
+// 2D byte tensor [rows, Kb] with a (128 B x box_rows) box and 128 B swizzle; out-of-range rows read as zero
+bool encode_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t Kb, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {Kb, rows};
+    const cuuint64_t strides[1] = {Kb};
+    const cuuint32_t box[2] = {(cuuint32_t)BKB, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+std::mutex g_map_mutex;
+std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> g_map_cache;  // weights are long-lived
+
+bool cached_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t Kb, uint32_t box_rows) {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto key = std::make_tuple(ptr, rows, Kb, box_rows);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+        *map = it->second;
+        return true;
+    }
+    if (!encode_map(map, ptr, rows, Kb, box_rows)) return false;
+    if (g_map_cache.size() > 4096) g_map_cache.clear();
+    g_map_cache[key] = *map;
+    return true;
+}
+
+template <bool I8, int EPI, int BN>
+int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* w, const float* w_scale, int64_t M, int N,
+               int Kb, void* out, int64_t ldc) {
+    using C = Cfg<BN>;
+    auto kern = gemm_tc_kernel<I8, EPI, BN>;
+    static bool configured = false;
+    if (!configured) {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    CUtensorMap ma, mw;
+    B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)Kb, BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
+    B2_REQUIRE(cached_map(&mw, w, (uint64_t)N, (uint64_t)Kb, BN), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W) failed");
+    const int tiles = (int)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+template <bool I8, int EPI>
+int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void* w, const float* w_scale, int64_t M, int N,
+                int Kb, void* out, int64_t ldc) {
+    // wave efficiency of the persistent schedule for both tile widths
+    auto eff = [&](int bn) {
+        const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+        const int64_t rounds = (tiles + g_num_sms - 1) / g_num_sms;
+        const double useful = (double)M * N / ((double)((M + BM - 1) / BM * BM) * ((N + bn - 1) / bn * bn));
+        return useful * (double)tiles / (double)(rounds * g_num_sms);
+    };
+    if (N >= 256 && eff(256) >= eff(128) * 0.97)
+        return launch<I8, EPI, 256>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+    return launch<I8, EPI, 128>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+}
+
+}  // namespace
+
+bool gemm_tc_available() {
+    init_once();
+    return g_encode != nullptr && g_num_sms > 0;
+}
+
+int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w, const float* w_scale,
+                       int64_t M, int N, int K, int epilogue, void* out, int64_t ldc) {
+    if (!gemm_tc_available()) {
+        set_last_error("tcgen05 gemm: needs an sm_100 device and cuTensorMapEncodeTiled");
+        return B2LLM_ERR_UNSUPPORTED;
+    }
+    const int Kb = is_i8 ? K : 2 * K;
+    // shapes outside the kernel's envelope go to the mma.sync baseline
+    if (Kb % BKB != 0 || N % 32 != 0 || M >= (1ll << 31) || ((uintptr_t)a & 15) || ((uintptr_t)w & 15) ||
+        ((uintptr_t)out & 15) || (ldc % 8) != 0) {
+        set_last_error("tcgen05 gemm: shape / alignment outside the kernel envelope");
+        return B2LLM_ERR_UNSUPPORTED;
+    }
+    if (M == 0) return B2LLM_OK;
+    if (is_i8) {
+        switch (epilogue) {
+            case EPI_F16: return pick_bn<true, EPI_F16>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+            case EPI_RESIDUAL: return pick_bn<true, EPI_RESIDUAL>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+            case EPI_SWIGLU: return pick_bn<true, EPI_SWIGLU>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+            default: break;
+        }
+    } else {
+        switch (epilogue) {
+            case EPI_F16: return pick_bn<false, EPI_F16>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
+            case EPI_RESIDUAL: return pick_bn<false, EPI_RESIDUAL>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
+            case EPI_SWIGLU: return pick_bn<false, EPI_SWIGLU>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
+            case EPI_F32: return pick_bn<false, EPI_F32>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
+            default: break;
+        }
+    }
+    set_last_error("tcgen05 gemm: unsupported epilogue");
     return B2LLM_ERR_UNSUPPORTED;
 }
+
 }  // namespace b2llm

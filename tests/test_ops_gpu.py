@@ -131,8 +131,11 @@ def test_gemm_w8a8_f16_bit_exact(lib, impl, M, N, K):
         pytest.skip("tcgen05 path not built")
     a, w, sa, sw = _gemm_inputs(M, N, K, M + N + K)
     out = torch.zeros((M, N), dtype=torch.float16, device="cuda")
-    capi.check(lib.b2llm_op_gemm_w8a8(stream_ptr(), _ptr(dev(a)), _ptr(dev(sa)), _ptr(dev(w)), _ptr(dev(sw)), M, N, K,
-                                      capi.EPI_F16, _ptr(out), impl), "gemm")
+    rc = lib.b2llm_op_gemm_w8a8(stream_ptr(), _ptr(dev(a)), _ptr(dev(sa)), _ptr(dev(w)), _ptr(dev(sw)), M, N, K,
+                                capi.EPI_F16, _ptr(out), impl)
+    if impl == 2 and rc == 4 and K % 128 != 0:
+        pytest.skip("K outside the tcgen05 kernel's envelope (falls back to the mma.sync kernel when impl = 0)")
+    capi.check(rc, "gemm")
     sync()
     exp = ref.dequant_acc(ref.gemm_i8_acc(a, w), sa, sw).astype(np.float16)
     assert np.array_equal(out.cpu().numpy().view(np.uint16), exp.view(np.uint16))
