@@ -1,23 +1,35 @@
 // K6 (+K7 reference form) of SURVEY.md section 2.3: attention over the paged / indexed int8 KV cache.
 //
-//  * attn_decode_mma_kernel -- THE dominant kernel of the decode step (HBM-bound: it streams
-//    kv_len * 320 B per (sequence, kv head)).  One CTA per (sequence, kv head, kv split); 4 warps,
-//    each with a private 3-stage cp.async ring of 16-token units (K 2 KB + V 2 KB + scales 1 KB), so
-//    warps never block each other and ~60 KB per CTA are in flight.  Rows of 128 B (one token-head)
-//    are fetched as 8 coalesced 16 B chunks into XOR-swizzled shared memory.  int8 -> fp16 dequant
-//    happens in registers (magic-number trick: (b ^ 0x80) | 0x6400 == 1024 + (b + 128), minus 1152,
-//    times the group scale) directly into mma.sync m16n8k16 fragments:
+//  * attn_decode_kernel -- THE dominant kernel of the decode step (HBM-bound: it streams
+//    kv_len * 320 B per (sequence, kv head)).  One CTA per (sequence, kv head [, q-head chunk], kv split);
+//    every warp owns a private 3-stage ring of 16-token units (K 2 KB + V 2 KB + scales 1 KB) and
+//    never synchronises with the other warps until the final merge.  Two loaders fill the ring:
+//      - TMA (default): one lane issues four cp.async.bulk.tensor 3D loads per unit -- a 16-token x
+//        128 B box of the int8 cache (128-byte swizzle) for K and V, and 16 x 32 B of fp16 scales for
+//        each -- against tensor maps that describe any of the reference's four cache layouts;
+//        completion through a per-stage mbarrier (complete_tx).  Needs the 16 tokens of a unit to be
+//        contiguous slots: cache_mode 0, or paging with page_size % 16 == 0.
+//      - cp.async (fallback for other page sizes): 10 x 16 B LDGSTS per lane per unit, same smem image.
+//    int8 -> fp16 dequant happens in registers (magic-number trick: (b ^ 0x80) | 0x6400 is the half
+//    1024 + (b + 128); minus 1152, times the group scale) directly into mma.sync m16n8k16 fragments:
 //        S[q-head, token]  = Q[q-head, d]   . K^T[d, token]     (A = Q, B = K as stored: token-major)
-//        O[q-head, d]      = P[q-head, tok] . V[tok, d]         (A = P from S's accumulator layout)
+//        O[q-head, d]      = P[q-head, tok] . V[tok, d]         (A = P from S's accumulator layout,
+//                                                                as hi + lo fp16 halves)
 //    the head-dim and token orders inside a fragment are permuted so that every lane reads whole
-//    16-byte chunks; fp32 accumulation, online softmax in the exp2 domain, split-KV partials merged
-//    by attn_merge_kernel.  GQA packs up to 8 q-heads of a kv head into the MMA M dimension.
+//    16-byte chunks, conflict-free under the 128 B swizzle; fp32 accumulation, online softmax in the
+//    exp2 domain, split-KV partials merged by attn_merge_kernel.  GQA packs up to 8 q-heads of a kv
+//    head into the MMA M dimension.
 //  * attn_simple_kernel -- one warp per (token, q-head), straightforward fp32 math.  Reference form
 //    used for prefill tokens (fresh fp16 K/V + optional cached prefix) and as the checker of the
 //    MMA kernel (impl = 1).
 //
 // Numeric contract: oracle/llama_ref.py attention_decode / _attend.
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace b2llm {
 
@@ -119,11 +131,14 @@ constexpr int UNIT = 16;                 // tokens per warp iteration
 constexpr int NSTAGE = 3;
 constexpr int K_BYTES = UNIT * 128;      // 2048
 constexpr int S_BYTES = UNIT * 32;       // 512 (16 fp16 scales per token)
-constexpr int STAGE = 2 * K_BYTES + 2 * S_BYTES;  // 5120
-constexpr int WARPS = 4;
-constexpr int ATT_SMEM = WARPS * NSTAGE * STAGE;  // 61440
+constexpr int STAGE = 2 * K_BYTES + 2 * S_BYTES;  // 5120: K | V | K scales | V scales
+constexpr int MAX_WARPS = 4;
 
-__device__ __forceinline__ int swz_f(int r) { return (r & 6) ^ ((r & 1) << 2); }
+struct DecodeTma {          // coordinates of the TMA loader (see make_kv_maps)
+    int tok_dim;            // 1: tokens run along tensor dim 1 (layout 3), 2: along dim 2 (layouts 0..2)
+    int k_fixed, v_fixed;   // the non-token coordinate for K / V of head 0 (+ head index in the kernel)
+    int k_tok0, v_tok0;     // token coordinate base for K / V
+};
 
 __device__ __forceinline__ uint32_t lop3_and_xor(uint32_t x, uint32_t m, uint32_t k) {
     uint32_t r;
@@ -143,9 +158,138 @@ __device__ __forceinline__ uint32_t deq2(uint32_t e, __half2 sc) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int G>  // q heads per CTA (rows of the MMA M dimension in use), 1..8
-__global__ void __launch_bounds__(WARPS * 32, 3) attn_decode_mma_kernel(AttnParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+// smem image of a 16-token x 128 B tile: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+// (exactly what TMA's 128-byte swizzle produces; the cp.async loader writes the same image)
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct WarpState {
+    float o[8][4];          // O^T fragments: m-tile i holds d = 16 g + i (regs 0,1) and 16 g + 8 + i (regs 2,3) x heads 2t, 2t+1
+    float m_run[2], l_run[2];  // running max / per-lane partial sum for heads 2t and 2t + 1
+};
+
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+    return d;
+}
+__device__ __forceinline__ void mma_f16_full(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    mma_f16_16816(d, a0, a1, a2, a3, b0, b1);
+}
+
+// one 16-token unit in the "transposed" formulation (tokens / head-dims fill the MMA M dimension, the
+// q heads of the kv head the N dimension):
+//     S^T[token, head] = K[token, d] . Q^T[d, head]          A = dequantised K rows (all 4 fragment regs live)
+//     O^T[d, head]    += V^T[d, token] . P^T[token, head]    A = dequantised V (token pairs gathered by PRMT),
+//                                                            B = P moved from accumulator to operand layout
+//                                                                by movmatrix.trans, as hi + lo fp16 halves
+__device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, const uint32_t (&qb)[8][2], WarpState& st,
+                                             int tbase, int kv_len, float sl2, int g, int t) {
+    const uint8_t* sK = stage;
+    const uint8_t* sV = stage + K_BYTES;
+    const uint8_t* sKS = stage + 2 * K_BYTES;
+    const uint8_t* sVS = sKS + S_BYTES;
+
+    // ---- S^T: lane (g, t) dequantises bytes [32 t, 32 t + 32) of token rows g and g + 8
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const uint4 ca = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t));
+        const uint4 cb = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t + 1));
+        const uint4 cc = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t));
+        const uint4 cd = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t + 1));
+        const uint2 sc_lo = *reinterpret_cast<const uint2*>(sKS + g * 32 + 8 * t);        // groups 4t .. 4t+3 of token g
+        const uint2 sc_hi = *reinterpret_cast<const uint2*>(sKS + (g + 8) * 32 + 8 * t);  // ... of token g + 8
+        const uint32_t w_lo[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        const uint32_t w_hi[8] = {cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
+        const __half2 l01 = *reinterpret_cast<const __half2*>(&sc_lo.x), l23 = *reinterpret_cast<const __half2*>(&sc_lo.y);
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&sc_hi.x), h23 = *reinterpret_cast<const __half2*>(&sc_hi.y);
+        const __half2 s_lo[4] = {__low2half2(l01), __high2half2(l01), __low2half2(l23), __high2half2(l23)};
+        const __half2 s_hi[4] = {__low2half2(h01), __high2half2(h01), __low2half2(h23), __high2half2(h23)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t a0 = deq2(lop3_and_xor(w_lo[j], 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);       // token g, bytes 0,2
+            const uint32_t a2 = deq2(lop3_and_xor(w_lo[j] >> 8, 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);  // token g, bytes 1,3
+            const uint32_t a1 = deq2(lop3_and_xor(w_hi[j], 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);       // token g + 8
+            const uint32_t a3 = deq2(lop3_and_xor(w_hi[j] >> 8, 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);
+            mma_f16_full(s_acc, a0, a1, a2, a3, qb[j][0], qb[j][1]);
+        }
+    }
+
+    // ---- online softmax per head column c (heads 2t + c) over the 16 tokens (rows g and g + 8 of all lanes)
+    const bool ok0 = tbase + g < kv_len, ok1 = tbase + g + 8 < kv_len;
+    float sv[2][2], pv[2][2];
+    bool moved = false;
+    float m_safe[2], m_new[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        sv[c][0] = ok0 ? s_acc[c] * sl2 : -INFINITY;
+        sv[c][1] = ok1 ? s_acc[2 + c] * sl2 : -INFINITY;
+        float mx = fmaxf(sv[c][0], sv[c][1]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        m_new[c] = fmaxf(st.m_run[c], mx);
+        moved |= m_new[c] != st.m_run[c];
+        m_safe[c] = m_new[c] == -INFINITY ? 0.f : m_new[c];
+        pv[c][0] = exp2f(sv[c][0] - m_safe[c]);
+        pv[c][1] = exp2f(sv[c][1] - m_safe[c]);
+    }
+    if (__any_sync(0xffffffffu, moved)) {  // some running max moved: rescale (rare after the first units)
+        const float c0 = exp2f(st.m_run[0] - m_safe[0]), c1 = exp2f(st.m_run[1] - m_safe[1]);
+        st.l_run[0] *= c0;
+        st.l_run[1] *= c1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            st.o[i][0] *= c0; st.o[i][1] *= c1; st.o[i][2] *= c0; st.o[i][3] *= c1;
+        }
+        st.m_run[0] = m_new[0];
+        st.m_run[1] = m_new[1];
+    }
+    st.l_run[0] += pv[0][0] + pv[0][1];
+    st.l_run[1] += pv[1][0] + pv[1][1];
+
+    // P: accumulator layout (row = token, cols = heads 2t, 2t+1) -> B operand layout (row = head g, cols =
+    // tokens 2t, 2t+1) with movmatrix.trans; hi + lo fp16 halves keep ~22 bits of P
+    __half2 ph0 = __floats2half2_rn(pv[0][0], pv[1][0]), ph1 = __floats2half2_rn(pv[0][1], pv[1][1]);
+    const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
+    __half2 pl0 = __floats2half2_rn(pv[0][0] - f0.x, pv[1][0] - f0.y), pl1 = __floats2half2_rn(pv[0][1] - f1.x, pv[1][1] - f1.y);
+    const uint32_t bh0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph0)), bh1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph1));
+    const uint32_t bl0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl0)), bl1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl1));
+
+    // ---- O^T += V^T P^T: lane (g, t) dequantises bytes [16 g, 16 g + 16) of token rows {2t, 2t+1, 8+2t, 9+2t}
+    const int r0 = 2 * t, r1 = 2 * t + 1, r2 = 8 + 2 * t, r3 = 9 + 2 * t;
+    const uint4 va = *reinterpret_cast<const uint4*>(sV + tile_off(r0, g));
+    const uint4 vb = *reinterpret_cast<const uint4*>(sV + tile_off(r1, g));
+    const uint4 vc = *reinterpret_cast<const uint4*>(sV + tile_off(r2, g));
+    const uint4 vd = *reinterpret_cast<const uint4*>(sV + tile_off(r3, g));
+    const uint32_t sA = *reinterpret_cast<const uint32_t*>(sVS + r0 * 32 + 4 * g);  // groups 2g, 2g+1
+    const uint32_t sB = *reinterpret_cast<const uint32_t*>(sVS + r1 * 32 + 4 * g);
+    const uint32_t sC = *reinterpret_cast<const uint32_t*>(sVS + r2 * 32 + 4 * g);
+    const uint32_t sD = *reinterpret_cast<const uint32_t*>(sVS + r3 * 32 + 4 * g);
+    uint32_t u_ab[2] = {prmt(sA, sB, 0x5410), prmt(sA, sB, 0x7632)};  // (A, B) scales of group 2g / 2g+1
+    uint32_t u_cd[2] = {prmt(sC, sD, 0x5410), prmt(sC, sD, 0x7632)};
+    const __half2 s_ab0 = *reinterpret_cast<__half2*>(&u_ab[0]), s_ab1 = *reinterpret_cast<__half2*>(&u_ab[1]);
+    const __half2 s_cd0 = *reinterpret_cast<__half2*>(&u_cd[0]), s_cd1 = *reinterpret_cast<__half2*>(&u_cd[1]);
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wdd[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int w = i >> 2, bsel = i & 3;
+        const uint32_t sel = (uint32_t)(bsel | (bsel << 4) | ((4 + bsel) << 8) | ((4 + bsel) << 12));
+        const uint32_t a0 = deq2(lop3_and_xor(prmt(wa[w], wb[w], sel), 0x00FF00FFu, 0x64806480u), s_ab0);            // d = 16g + i
+        const uint32_t a1 = deq2(lop3_and_xor(prmt(wa[w + 2], wb[w + 2], sel), 0x00FF00FFu, 0x64806480u), s_ab1);    // d = 16g + 8 + i
+        const uint32_t a2 = deq2(lop3_and_xor(prmt(wc[w], wdd[w], sel), 0x00FF00FFu, 0x64806480u), s_cd0);
+        const uint32_t a3 = deq2(lop3_and_xor(prmt(wc[w + 2], wdd[w + 2], sel), 0x00FF00FFu, 0x64806480u), s_cd1);
+        mma_f16_full(st.o[i], a0, a1, a2, a3, bh0, bh1);
+        mma_f16_full(st.o[i], a0, a1, a2, a3, bl0, bl1);
+    }
+}
+
+template <int G, int WARPS, bool TMA>  // G: q heads per CTA (rows of the MMA M dimension in use), 1..8
+__global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
+    attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
+                       DecodeTma tc) {
+    extern __shared__ uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int split = blockIdx.x, b = blockIdx.z;
@@ -155,23 +299,37 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_decode_mma_kernel(AttnPara
     const int hq0 = hk * gq + (blockIdx.y % chunks) * G;
     const int nrow = min(G, hk * gq + gq - hq0);  // valid q-head rows
 
-    const int64_t kv_len = p.start_pos[b] + 1;
-    const int64_t units_total = (kv_len + UNIT - 1) / UNIT;
-    const int64_t units_per_split = (units_total + p.nsplit - 1) / p.nsplit;
-    const int64_t u0 = split * units_per_split;
-    const int64_t u1 = min(units_total, u0 + units_per_split);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024 B alignment
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + WARPS * NSTAGE * STAGE;
+
+    const int kv_len = (int)(p.start_pos[b] + 1);
+    const int units_total = (kv_len + UNIT - 1) / UNIT;
+    const int units_per_split = (units_total + p.nsplit - 1) / p.nsplit;
+    const int u0 = split * units_per_split;
+    const int u1 = min(units_total, u0 + units_per_split);
 
     const int heads = p.nq + 2 * p.nkv;
     const int64_t tok = b;  // decode sequences come first, one token each (seq_starts[b] == b)
 
-    // ---- Q fragments (A operand), rows >= nrow are zero.  k-slot order follows the K byte order:
-    // step j, lane t covers d = base(j,t) + {0,2} (A0) and {1,3} (A2), base = (j<4 ? 16t : 64+16t) + 4(j&3)
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < WARPS * NSTAGE; ++i) mbar_init(bars + 8u * i, 1);
+            mbar_fence_init();
+            tma_prefetch_desc(&map_kv);
+            tma_prefetch_desc(&map_sc);
+        }
+        __syncthreads();
+    }
+
+    // ---- Q^T fragments (B operand, column n = g is q head hq0 + g; columns >= nrow are zero).  k-slot
+    // order follows the K byte order: step j, lane t covers d = 32 t + 4 j + {0,2} (b0) and {1,3} (b1)
     uint32_t qa[8][2];
     {
         const __half* qrow = p.qkv + tok * (int64_t)heads * 128 + (int64_t)(hq0 + g) * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int base = (j < 4 ? 16 * t : 64 + 16 * t) + 4 * (j & 3);
+            const int base = 32 * t + 4 * j;
             if (g < nrow) {
                 const uint2 v = *reinterpret_cast<const uint2*>(qrow + base);  // halves d..d+3
                 qa[j][0] = prmt(v.x, v.y, 0x5410);  // (d+0, d+2)
@@ -183,176 +341,176 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_decode_mma_kernel(AttnPara
         }
     }
 
+    uint8_t* wsm = smem + warp * (NSTAGE * STAGE);
+    const uint32_t wsm_u32 = smem_base + warp * (NSTAGE * STAGE);
+    const uint32_t wbar = bars + 8u * (warp * NSTAGE);
+
+    // page-table walk: first cache slot of unit u (its 16 tokens are contiguous slots on the TMA path)
+    auto unit_slot0 = [&](int u) -> int64_t {
+        const int pos = u * UNIT;
+        if (p.cache_mode == 0) return p.cache_indices[b] + pos;
+        return p.cache_indices[(int64_t)b * p.max_pages + pos / p.page_size] + pos % p.page_size;
+    };
+
+    // ---- loader: fill stage `st` of this warp's ring with unit u
     const int8_t* kbase = p.cache + hk * p.cs.head;
     const int8_t* vbase = kbase + p.cs.kv;
     const __half* ksbase = p.scale + hk * p.cs.head / 8;
     const __half* vsbase = ksbase + p.cs.kv / 8;
-    uint8_t* wsm = smem + warp * (NSTAGE * STAGE);
-    const uint32_t wsm_u32 = smem_u32(wsm);
-
-    // issue the loads of unit u into stage st (warp-collective; 10 x 16 B per lane)
-    auto load_unit = [&](int64_t u, int st) {
+    auto load_unit = [&](int u, int st) {
         const uint32_t sK = wsm_u32 + st * STAGE, sV = sK + K_BYTES, sKS = sV + K_BYTES, sVS = sKS + S_BYTES;
-        // lanes 0..15 look up the slot of token u*16 + lane
-        int64_t myslot = -1;
-        {
-            const int64_t pos = u * UNIT + (lane & 15);
-            if (pos < kv_len) myslot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
-        }
+        if constexpr (TMA) {
+            if (lane == 0) {
+                const int s0 = (int)unit_slot0(u);
+                const uint32_t bar = wbar + 8u * st;
+                mbar_expect_tx(bar, STAGE);
+                if (tc.tok_dim == 1) {
+                    tma_load_3d(sK, &map_kv, bar, 0, tc.k_tok0 + s0, tc.k_fixed + hk);
+                    tma_load_3d(sV, &map_kv, bar, 0, tc.v_tok0 + s0, tc.v_fixed + hk);
+                    tma_load_3d(sKS, &map_sc, bar, 0, tc.k_tok0 + s0, tc.k_fixed + hk);
+                    tma_load_3d(sVS, &map_sc, bar, 0, tc.v_tok0 + s0, tc.v_fixed + hk);
+                } else {
+                    tma_load_3d(sK, &map_kv, bar, 0, tc.k_fixed + hk, tc.k_tok0 + s0);
+                    tma_load_3d(sV, &map_kv, bar, 0, tc.v_fixed + hk, tc.v_tok0 + s0);
+                    tma_load_3d(sKS, &map_sc, bar, 0, tc.k_fixed + hk, tc.k_tok0 + s0);
+                    tma_load_3d(sVS, &map_sc, bar, 0, tc.v_fixed + hk, tc.v_tok0 + s0);
+                }
+            }
+        } else {
+            // lanes 0..15 look up the slot of token u*16 + lane
+            int64_t myslot = -1;
+            {
+                const int pos = u * UNIT + (lane & 15);
+                if (pos < kv_len) myslot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = (lane >> 3) + 4 * i, c = lane & 7;
-            const int64_t slot = __shfl_sync(0xffffffffu, myslot, r);
-            const int ok = slot >= 0 ? 16 : 0;
-            const int64_t off = (slot >= 0 ? slot : 0) * p.cs.tok + c * 16;
-            const uint32_t d = r * 128 + ((c ^ swz_f(r)) << 4);
-            cp_async16(sK + d, kbase + off, ok);
-            cp_async16(sV + d, vbase + off, ok);
-        }
-        {
-            const int r = lane >> 1, c = lane & 1;
-            const int64_t slot = __shfl_sync(0xffffffffu, myslot, r);
-            const int ok = slot >= 0 ? 16 : 0;
-            const int64_t off = (slot >= 0 ? slot : 0) * (p.cs.tok / 8) + c * 8;  // fp16 elements
-            cp_async16(sKS + r * 32 + c * 16, ksbase + off, ok);
-            cp_async16(sVS + r * 32 + c * 16, vsbase + off, ok);
+            for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 3) + 4 * i, c = lane & 7;
+                const int64_t slot = __shfl_sync(0xffffffffu, myslot, r);
+                const int ok = slot >= 0 ? 16 : 0;
+                const int64_t off = (slot >= 0 ? slot : 0) * p.cs.tok + c * 16;
+                cp_async16(sK + tile_off(r, c), kbase + off, ok);
+                cp_async16(sV + tile_off(r, c), vbase + off, ok);
+            }
+            {
+                const int r = lane >> 1, c = lane & 1;
+                const int64_t slot = __shfl_sync(0xffffffffu, myslot, r);
+                const int ok = slot >= 0 ? 16 : 0;
+                const int64_t off = (slot >= 0 ? slot : 0) * (p.cs.tok / 8) + c * 8;  // fp16 elements
+                cp_async16(sKS + r * 32 + c * 16, ksbase + off, ok);
+                cp_async16(sVS + r * 32 + c * 16, vsbase + off, ok);
+            }
         }
     };
 
-    float o[16][4];
+    WarpState st;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) o[j][r] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;   // state of q-head row g (replicated over the 4 t-lanes; l is per-lane partial)
+        for (int r = 0; r < 4; ++r) st.o[j][r] = 0.f;
+    st.m_run[0] = st.m_run[1] = -INFINITY;
+    st.l_run[0] = st.l_run[1] = 0.f;  // per-lane partials of the sums of heads 2t, 2t + 1
     const float sl2 = p.sm_scale * 1.4426950408889634f;
 
-    // prologue
-    int64_t u_issue = u0 + warp;
+    // prologue: NSTAGE - 1 units in flight
+    int u_issue = u0 + warp;
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
         if (u_issue < u1) load_unit(u_issue, s);
-        cp_async_commit();
+        if constexpr (!TMA) cp_async_commit();
         u_issue += WARPS;
     }
-    int st = 0;
-    for (int64_t u = u0 + warp; u < u1; u += WARPS) {
-        cp_async_wait<NSTAGE - 2>();
+    int stg = 0;
+    uint32_t phase = 0;
+    for (int u = u0 + warp; u < u1; u += WARPS) {
+        if constexpr (TMA) {
+            mbar_wait(wbar + 8u * stg, phase);
+        } else {
+            cp_async_wait<NSTAGE - 2>();
+        }
         __syncwarp();
         {   // refill the stage consumed in the previous iteration
-            const int st_next = (st + NSTAGE - 1) % NSTAGE;
+            const int st_next = (stg + NSTAGE - 1) % NSTAGE;
             if (u_issue < u1) load_unit(u_issue, st_next);
-            cp_async_commit();
+            if constexpr (!TMA) cp_async_commit();
             u_issue += WARPS;
         }
-        const uint8_t* sK = wsm + st * STAGE;
-        const uint8_t* sV = sK + K_BYTES;
-        const uint8_t* sKS = sV + K_BYTES;
-        const uint8_t* sVS = sKS + S_BYTES;
-
-        // ---- S = Q K^T for 2 n-tiles of 8 tokens
-        float s_acc[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) s_acc[nt][r] = 0.f;
-            const int r = 8 * nt + g;
-            const uint4 ca = *reinterpret_cast<const uint4*>(sK + r * 128 + ((t ^ swz_f(r)) << 4));
-            const uint4 cb = *reinterpret_cast<const uint4*>(sK + r * 128 + (((4 + t) ^ swz_f(r)) << 4));
-            const __half2 sa = *reinterpret_cast<const __half2*>(sKS + r * 32 + 4 * t);        // groups 2t, 2t+1
-            const __half2 sb = *reinterpret_cast<const __half2*>(sKS + r * 32 + 16 + 4 * t);   // groups 8+2t, 8+2t+1
-            const uint32_t wds[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-            const __half2 scs[4] = {__low2half2(sa), __high2half2(sa), __low2half2(sb), __high2half2(sb)};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t wd = wds[j];
-                const uint32_t b0 = deq2(lop3_and_xor(wd, 0x00FF00FFu, 0x64806480u), scs[j >> 1]);       // bytes 0,2
-                const uint32_t b1 = deq2(lop3_and_xor(wd >> 8, 0x00FF00FFu, 0x64806480u), scs[j >> 1]);  // bytes 1,3
-                mma_f16_16816(s_acc[nt], qa[j][0], 0u, qa[j][1], 0u, b0, b1);
+        uint8_t* stage = wsm + stg * STAGE;
+        if constexpr (TMA) {
+            // the tail unit's rows past kv_len hold whatever the cache holds there: neutralise their V scales
+            // (their scores are masked to -inf below; 0 * NaN must not reach the accumulator)
+            const int valid = kv_len - u * UNIT;
+            if (valid < UNIT) {
+                if (lane >= valid && lane < UNIT) {
+                    uint4* row = reinterpret_cast<uint4*>(stage + 2 * K_BYTES + S_BYTES + lane * 32);
+                    row[0] = make_uint4(0, 0, 0, 0);
+                    row[1] = make_uint4(0, 0, 0, 0);
+                }
+                __syncwarp();
             }
         }
-
-        // ---- online softmax for q-head row g over tokens {2t, 2t+1, 8+2t, 9+2t} of this unit
-        const int64_t tbase = u * UNIT;
-        float sv[4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int64_t pos = tbase + 8 * nt + 2 * t + c;
-                sv[nt * 2 + c] = pos < kv_len ? s_acc[nt][c] * sl2 : -INFINITY;
-            }
-        float mx = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_run, mx);
-        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-        const float corr = exp2f(m_run - m_safe);
-        float pv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pv[i] = exp2f(sv[i] - m_safe);
-        l_run = l_run * corr + (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        m_run = m_new;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            o[j][0] *= corr;
-            o[j][1] *= corr;
-        }
-        // P enters the tensor core as hi + lo fp16 halves (~22 significant bits), so the only fp16
-        // roundings on this path are the dequantised K / V values, which the oracle reproduces
-        __half2 p01 = __floats2half2_rn(pv[0], pv[1]), p23 = __floats2half2_rn(pv[2], pv[3]);
-        const float2 f01 = __half22float2(p01), f23 = __half22float2(p23);
-        __half2 q01 = __floats2half2_rn(pv[0] - f01.x, pv[1] - f01.y), q23 = __floats2half2_rn(pv[2] - f23.x, pv[3] - f23.y);
-        const uint32_t pa0 = *reinterpret_cast<uint32_t*>(&p01), pa2 = *reinterpret_cast<uint32_t*>(&p23);
-        const uint32_t pl0 = *reinterpret_cast<uint32_t*>(&q01), pl2 = *reinterpret_cast<uint32_t*>(&q23);
-
-        // ---- O += P V : lane (g, t) supplies column n = g of every n-tile, i.e. d = 16 g + j, for tokens
-        // {2t, 2t+1} (B0) and {8+2t, 9+2t} (B1)
-        {
-            const int r0 = 2 * t, r1 = 2 * t + 1, r2 = 8 + 2 * t, r3 = 9 + 2 * t;
-            const uint4 va = *reinterpret_cast<const uint4*>(sV + r0 * 128 + ((g ^ swz_f(r0)) << 4));
-            const uint4 vb = *reinterpret_cast<const uint4*>(sV + r1 * 128 + ((g ^ swz_f(r1)) << 4));
-            const uint4 vc = *reinterpret_cast<const uint4*>(sV + r2 * 128 + ((g ^ swz_f(r2)) << 4));
-            const uint4 vd = *reinterpret_cast<const uint4*>(sV + r3 * 128 + ((g ^ swz_f(r3)) << 4));
-            const uint32_t sA = *reinterpret_cast<const uint32_t*>(sVS + r0 * 32 + 4 * g);  // groups 2g, 2g+1
-            const uint32_t sB = *reinterpret_cast<const uint32_t*>(sVS + r1 * 32 + 4 * g);
-            const uint32_t sC = *reinterpret_cast<const uint32_t*>(sVS + r2 * 32 + 4 * g);
-            const uint32_t sD = *reinterpret_cast<const uint32_t*>(sVS + r3 * 32 + 4 * g);
-            uint32_t sc_ab[2] = {prmt(sA, sB, 0x5410), prmt(sA, sB, 0x7632)};  // (A.lo,B.lo), (A.hi,B.hi)
-            uint32_t sc_cd[2] = {prmt(sC, sD, 0x5410), prmt(sC, sD, 0x7632)};
-            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-            const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wdd[4] = {vd.x, vd.y, vd.z, vd.w};
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int w = j >> 2, i = j & 3;
-                const uint32_t sel = (uint32_t)(i | (i << 4) | ((4 + i) << 8) | ((4 + i) << 12));
-                const __half2 s_ab = *reinterpret_cast<__half2*>(&sc_ab[j >> 3]);
-                const __half2 s_cd = *reinterpret_cast<__half2*>(&sc_cd[j >> 3]);
-                const uint32_t b0 = deq2(lop3_and_xor(prmt(wa[w], wb[w], sel), 0x00FF00FFu, 0x64806480u), s_ab);
-                const uint32_t b1 = deq2(lop3_and_xor(prmt(wc[w], wdd[w], sel), 0x00FF00FFu, 0x64806480u), s_cd);
-                mma_f16_16816(o[j], pa0, 0u, pa2, 0u, b0, b1);
-                mma_f16_16816(o[j], pl0, 0u, pl2, 0u, b0, b1);
-            }
-        }
-        st = (st + 1) % NSTAGE;
+        process_unit(stage, qa, st, u * UNIT, kv_len, sl2, g, t);
+        if (++stg == NSTAGE) { stg = 0; phase ^= 1; }
     }
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
 
-    // ---- reduce l over the 4 t-lanes, then merge the 4 warps through shared memory
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    // ---- reduce the row sums over the 8 g-lanes; lane (g, t) then owns d = [16 g, 16 g + 16) of heads 2t, 2t + 1
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        st.l_run[c] += __shfl_xor_sync(0xffffffffu, st.l_run[c], 4);
+        st.l_run[c] += __shfl_xor_sync(0xffffffffu, st.l_run[c], 8);
+        st.l_run[c] += __shfl_xor_sync(0xffffffffu, st.l_run[c], 16);
+    }
+    if constexpr (WARPS == 1) {
+        // single warp: normalise and store straight from the accumulator fragments (32 contiguous bytes per lane)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rq = 2 * t + c;
+            if (rq >= nrow) continue;
+            const int hq = hq0 + rq;
+            if (p.nsplit == 1) {
+                const float inv = 1.f / st.l_run[c];
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __half2 lo = __floats2half2_rn(st.o[2 * i][c] * inv, st.o[2 * i + 1][c] * inv);
+                    __half2 hi = __floats2half2_rn(st.o[2 * i][2 + c] * inv, st.o[2 * i + 1][2 + c] * inv);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&lo);
+                    pk[4 + i] = *reinterpret_cast<uint32_t*>(&hi);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.out + tok * (int64_t)p.nq * 128 + (int64_t)hq * 128 + 16 * g);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+                float* wrow = p.ws + (((int64_t)b * p.nq + hq) * p.nsplit + split) * 130;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    wrow[16 * g + i] = st.o[i][c];
+                    wrow[16 * g + 8 + i] = st.o[i][2 + c];
+                }
+                if (g == 0) {
+                    wrow[128] = st.m_run[c];
+                    wrow[129] = st.l_run[c];
+                }
+            }
+        }
+        return;
+    }
     __syncthreads();  // all rings are dead from here on
     float* red = reinterpret_cast<float*>(smem);  // [WARPS][G][130]: 128 o, m, l
-    if (g < G) {
-        float* row = red + (warp * G + g) * 130;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            row[16 * (2 * t) + j] = o[j][0];
-            row[16 * (2 * t + 1) + j] = o[j][1];
+    for (int c = 0; c < 2; ++c) {
+        const int rq = 2 * t + c;
+        if (rq >= G) continue;
+        float* row = red + (warp * G + rq) * 130;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            row[16 * g + i] = st.o[i][c];
+            row[16 * g + 8 + i] = st.o[i][2 + c];
         }
-        if (t == 0) {
-            row[128] = m_run;
-            row[129] = l_run;
+        if (g == 0) {
+            row[128] = st.m_run[c];
+            row[129] = st.l_run[c];
         }
     }
     __syncthreads();
@@ -407,7 +565,7 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict
 }
 
 int choose_splits(int64_t ctas_per_split, int64_t max_kv_len) {
-    // fill ~3 CTAs/SM on 148 SMs; never make a split shorter than 4 units per warp
+    // fill ~3 CTAs/SM on 148 SMs; never make a split shorter than 256 tokens
     const int64_t target = 148 * 3;
     int64_t n = (target + ctas_per_split - 1) / ctas_per_split;
     const int64_t max_by_len = (max_kv_len + 255) / 256;
@@ -443,6 +601,70 @@ AttnParams make_params(const AttnArgs& a) {
     return p;
 }
 
+// ---- tensor maps over the whole cache / scale tensors, one pair per (pointer, geometry).
+// Every layout of llm_engine.cc:118-169 is a 3-D byte tensor {row bytes, X, Y} whose boxes are
+// 16 token rows of one (layer, k/v, head):
+//   layout 3 [L,2,H,T,D]: {D, T, L*2*H}   box {D,16,1}   coords (0, slot, (l*2+kv)*H + h)
+//   layout 2 [L,2,T,H,D]: {D, H, L*2*T}   box {D,1,16}   coords (0, h, (l*2+kv)*T + slot)
+//   layout 1 [L,T,2,H,D]: {D, 2H, L*T}    box {D,1,16}   coords (0, kv*H + h, l*T + slot)
+//   layout 0 [T,L,2,H,D]: {D, L*2*H, T}   box {D,1,16}   coords (0, (l*2+kv)*H + h, slot)
+struct KvMaps {
+    CUtensorMap kv, sc;
+};
+std::mutex g_kvmap_mutex;
+std::map<std::tuple<const void*, const void*, int, int, int, int, uint64_t>, KvMaps> g_kvmap_cache;
+
+bool make_kv_maps(const AttnArgs& a, KvMaps* out) {
+    const b2llm_kv_geom& g = a.geom;
+    auto key = std::make_tuple((const void*)a.kv_cache, (const void*)a.kv_scale, g.cache_layout, g.num_layers, g.num_kv_heads,
+                               g.head_dim, (uint64_t)g.max_tokens);
+    std::lock_guard<std::mutex> lk(g_kvmap_mutex);
+    auto it = g_kvmap_cache.find(key);
+    if (it != g_kvmap_cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    const uint64_t L = g.num_layers, H = g.num_kv_heads, T = g.max_tokens;
+    for (int which = 0; which < 2; ++which) {
+        const uint64_t rb = which == 0 ? 128 : 32;  // row bytes: int8 values / fp16 scales
+        uint64_t dims[3], strides[2];
+        uint32_t box[3];
+        dims[0] = rb;
+        switch (g.cache_layout) {
+            case 3: dims[1] = T; dims[2] = L * 2 * H; box[1] = UNIT; box[2] = 1; break;
+            case 2: dims[1] = H; dims[2] = L * 2 * T; box[1] = 1; box[2] = UNIT; break;
+            case 1: dims[1] = 2 * H; dims[2] = L * T; box[1] = 1; box[2] = UNIT; break;
+            default: dims[1] = L * 2 * H; dims[2] = T; box[1] = 1; box[2] = UNIT; break;
+        }
+        box[0] = (uint32_t)rb;
+        strides[0] = rb;
+        strides[1] = rb * dims[1];
+        if (!tma_encode_bytes(which == 0 ? &out->kv : &out->sc, which == 0 ? (const void*)a.kv_cache : (const void*)a.kv_scale,
+                              3, dims, strides, box, which == 0))
+            return false;
+    }
+    if (g_kvmap_cache.size() > 64) g_kvmap_cache.clear();
+    g_kvmap_cache[key] = *out;
+    return true;
+}
+
+DecodeTma make_tma_coords(const AttnArgs& a) {
+    const b2llm_kv_geom& g = a.geom;
+    const int L = a.layer, H = g.num_kv_heads;
+    const int64_t T = (int64_t)g.max_tokens;
+    DecodeTma c{};
+    switch (g.cache_layout) {
+        case 3: c.tok_dim = 1; c.k_fixed = (L * 2 + 0) * H; c.v_fixed = (L * 2 + 1) * H; c.k_tok0 = 0; c.v_tok0 = 0; break;
+        case 2: c.tok_dim = 2; c.k_fixed = 0; c.v_fixed = 0; c.k_tok0 = (int)((L * 2 + 0) * T); c.v_tok0 = (int)((L * 2 + 1) * T); break;
+        case 1: c.tok_dim = 2; c.k_fixed = 0; c.v_fixed = H; c.k_tok0 = (int)(L * T); c.v_tok0 = (int)(L * T); break;
+        default: c.tok_dim = 2; c.k_fixed = (L * 2 + 0) * H; c.v_fixed = (L * 2 + 1) * H; c.k_tok0 = 0; c.v_tok0 = 0; break;
+    }
+    return c;
+}
+
+int g_attn_warps_override = -1, g_attn_tma_override = -1;
+std::once_flag g_attn_env_once;
+
 }  // namespace
 
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
@@ -471,20 +693,20 @@ int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token
     return B2LLM_OK;
 }
 
-template <int G>
-static int32_t launch_decode_g(cudaStream_t s, AttnParams& p, int64_t max_kv_len) {
-    auto kern = attn_decode_mma_kernel<G>;
+template <int G, int WARPS, bool TMA>
+static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc) {
+    auto kern = attn_decode_kernel<G, WARPS, TMA>;
+    constexpr int smem_bytes = WARPS * NSTAGE * STAGE + 1024 + 8 * WARPS * NSTAGE + 64 +
+                               (WARPS * G * 130 * 4 > WARPS * NSTAGE * STAGE ? WARPS * G * 130 * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     const int gq = p.nq / p.nkv;
     const int chunks = (gq + G - 1) / G;
-    const int64_t per_split = (int64_t)p.nkv * chunks * p.decoding_batches;
-    p.nsplit = choose_splits(per_split, max_kv_len);
     dim3 grid(p.nsplit, p.nkv * chunks, p.decoding_batches);
-    kern<<<grid, WARPS * 32, ATT_SMEM, s>>>(p);
+    kern<<<grid, WARPS * 32, smem_bytes, s>>>(p, maps.kv, maps.sc, tc);
     B2_LAUNCH_CHECK();
     if (p.nsplit > 1) {
         const int64_t rows = (int64_t)p.decoding_batches * p.nq;
@@ -494,17 +716,53 @@ static int32_t launch_decode_g(cudaStream_t s, AttnParams& p, int64_t max_kv_len
     return B2LLM_OK;
 }
 
+template <int G>
+static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc, int warps, bool tma) {
+    if (tma) {
+        if (warps == 1) return launch_decode<G, 1, true>(s, p, maps, tc);
+        if (warps == 2) return launch_decode<G, 2, true>(s, p, maps, tc);
+        return launch_decode<G, 4, true>(s, p, maps, tc);
+    }
+    if (warps == 1) return launch_decode<G, 1, false>(s, p, maps, tc);
+    if (warps == 2) return launch_decode<G, 2, false>(s, p, maps, tc);
+    return launch_decode<G, 4, false>(s, p, maps, tc);
+}
+
 int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     B2_REQUIRE(a.geom.head_dim == 128 && a.geom.quant_group == 8, B2LLM_ERR_UNSUPPORTED,
                "attention (tensor-core path): head_dim 128 and int8 group-8 cache only");
     B2_REQUIRE(a.step->decoding_batches <= 65535, B2LLM_ERR_INVALID_VALUE, "too many decoding sequences");
     if (a.step->decoding_batches == 0) return B2LLM_OK;
+    std::call_once(g_attn_env_once, [] {
+        if (const char* e = getenv("B2LLM_ATTN_WARPS")) g_attn_warps_override = atoi(e);
+        if (const char* e = getenv("B2LLM_ATTN_TMA")) g_attn_tma_override = atoi(e);
+    });
     AttnParams p = make_params(a);
     const int gq = p.nq / p.nkv;
     const int64_t max_kv = a.step->max_kv_len > 0 ? a.step->max_kv_len : 1;
-    if (gq == 1) return launch_decode_g<1>(s, p, max_kv);
-    if (gq <= 4) return launch_decode_g<4>(s, p, max_kv);
-    return launch_decode_g<8>(s, p, max_kv);
+    const int G = gq == 1 ? 1 : (gq <= 4 ? 4 : 8);
+    const int chunks = (gq + G - 1) / G;
+    p.nsplit = choose_splits((int64_t)p.nkv * chunks * p.decoding_batches, max_kv);
+    // warps per CTA: one warp per CTA is fastest (no cross-warp merge, measured on B200) as long as the
+    // grid alone fills the 148 x 12 warp slots; small grids get 2 or 4 warps per CTA
+    const int64_t ctas = (int64_t)p.nkv * chunks * p.decoding_batches * p.nsplit;
+    const int64_t units_per_cta = ((max_kv + UNIT - 1) / UNIT + p.nsplit - 1) / p.nsplit;
+    int warps = ctas >= 148 * 12 ? 1 : (ctas >= 148 * 6 || units_per_cta < 16 ? 2 : 4);
+    if (units_per_cta < 4) warps = 1;
+    if (g_attn_warps_override == 1 || g_attn_warps_override == 2 || g_attn_warps_override == 4) warps = g_attn_warps_override;
+    // TMA loader: units must be 16 contiguous slots
+    bool tma = tma_available() && (p.cache_mode == 0 || p.page_size % UNIT == 0) &&
+               (int64_t)a.geom.max_tokens * a.geom.num_layers * 2 < (1ll << 31);
+    if (g_attn_tma_override == 0) tma = false;
+    KvMaps maps{};
+    DecodeTma tc{};
+    if (tma) {
+        if (!make_kv_maps(a, &maps)) tma = false;
+        else tc = make_tma_coords(a);
+    }
+    if (G == 1) return dispatch_decode<1>(s, p, maps, tc, warps, tma);
+    if (G == 4) return dispatch_decode<4>(s, p, maps, tc, warps, tma);
+    return dispatch_decode<8>(s, p, maps, tc, warps, tma);
 }
 
 }  // namespace b2llm

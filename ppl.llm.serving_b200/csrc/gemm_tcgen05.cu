@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
+#include "tma_utils.cuh"
 
 namespace b2llm {
 
@@ -43,32 +44,7 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
+// ---------------------------------------------------------------- tcgen05 PTX wrappers (mbarrier / TMA ones: tma_utils.cuh)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -153,7 +129,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 128);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {  // whole warp allocates TMEM
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS));
@@ -166,8 +142,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w));
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_w);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -296,40 +272,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
-std::once_flag g_once;
-
-void init_once() {
-    std::call_once(g_once, [] {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            g_encode = (EncodeTiledFn)fn;
-        else
-            cudaGetLastError();
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10)
-            g_num_sms = prop.multiProcessorCount;
-        else
-            cudaGetLastError();
-    });
-}
-
 // 2D byte tensor [rows, Kb] with a (128 B x box_rows) box and 128 B swizzle; out-of-range rows read as zero
 bool encode_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t Kb, uint32_t box_rows) {
-    const cuuint64_t dims[2] = {Kb, rows};
-    const cuuint64_t strides[1] = {Kb};
-    const cuuint32_t box[2] = {(cuuint32_t)BKB, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const uint64_t dims[2] = {Kb, rows};
+    const uint64_t strides[1] = {Kb};
+    const uint32_t box[2] = {(uint32_t)BKB, box_rows};
+    return tma_encode_bytes(map, ptr, 2, dims, strides, box, true);
 }
 
 std::mutex g_map_mutex;
@@ -363,7 +311,7 @@ int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* 
     B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)Kb, BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
     B2_REQUIRE(cached_map(&mw, w, (uint64_t)N, (uint64_t)Kb, BN), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W) failed");
     const int tiles = (int)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
@@ -375,6 +323,7 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
     // wave efficiency of the persistent schedule for both tile widths
     auto eff = [&](int bn) {
         const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+        const int g_num_sms = device_num_sms();
         const int64_t rounds = (tiles + g_num_sms - 1) / g_num_sms;
         const double useful = (double)M * N / ((double)((M + BM - 1) / BM * BM) * ((N + bn - 1) / bn * bn));
         return useful * (double)tiles / (double)(rounds * g_num_sms);
@@ -386,10 +335,7 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
 
 }  // namespace
 
-bool gemm_tc_available() {
-    init_once();
-    return g_encode != nullptr && g_num_sms > 0;
-}
+bool gemm_tc_available() { return tma_available(); }
 
 int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w, const float* w_scale,
                        int64_t M, int N, int K, int epilogue, void* out, int64_t ldc) {
