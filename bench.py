@@ -310,7 +310,11 @@ def main():
                                                 "lm_head": ms_cls[2] / args.steps},
             },
             "roofline": {"kernel": "attn_decode_mma_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                         # exact shape (profiles/r1_ncu_attn.txt); null for any other shape
+                         "traffic": 5585427456 if (kv_len == 512 and cfg.num_layers == 32) else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": attn_bytes, "avg_launch_ms": attn_ms, "launches_timed": int(n_cls[0])},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

@@ -122,6 +122,21 @@ B2LLM_API int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t rank
                                       void* stream, b2llm_engine** out);
 B2LLM_API int32_t b2llm_engine_destroy(b2llm_engine* e);
 
+/* (re)size activation / staging buffers for steps of up to max_tokens tokens and max_batch sequences.  The
+ * reference gives these limits to the generator (GeneratorConfig, src/common/config.h:45-60), not to the
+ * runtime -- ppl.nn sizes buffers per step -- so the ppl::nn::Runtime adapter (host/src/pplnn_b200.cc) calls
+ * this lazily from Run().  Never shrinks; growth synchronises the engine stream. */
+B2LLM_API int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int64_t max_batch);
+
+/* replaces ppl::nn::Engine::Configure for the keys the reference sets (resource_manager.cc:74-112):
+ * key = B2LLM_CONF_*, value as documented per key.  Unknown keys -> B2LLM_ERR_UNSUPPORTED. */
+enum {
+    B2LLM_CONF_DECODING_ATTN_SPLIT_K = 3, /* 0 never split the KV range, 1 heuristic (default), 2 always */
+    B2LLM_CONF_ATTN_IMPL = 100,           /* 0 auto, 1 simple reference kernel, 2 tensor-core split-KV kernel */
+    B2LLM_CONF_GEMM_IMPL = 101            /* 0 auto, 1 mma.sync baseline, 2 tcgen05 */
+};
+B2LLM_API int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t value);
+
 /* weights.  load_weight takes the FULL (unsharded) fp16 tensor on the host and keeps this rank's
  * slice; with quant_method == online_i8i8 the projection weights are quantised per output channel on
  * load (the reference's "online" quantisation pass, resource_manager.cc:51-52).

@@ -56,6 +56,8 @@ SIGNATURES = {
     "b2llm_last_error": (C.c_char_p, []),
     "b2llm_engine_create": (_I32, [C.POINTER(ModelDescC), _I32, _I32, _P, _P, C.POINTER(_P)]),
     "b2llm_engine_destroy": (_I32, [_P]),
+    "b2llm_engine_reserve": (_I32, [_P, _I64, _I64]),
+    "b2llm_engine_configure": (_I32, [_P, _I32, _I64]),
     "b2llm_engine_load_weight": (_I32, [_P, _I32, _I32, _P, _U64]),
     "b2llm_engine_random_init": (_I32, [_P, _U64]),
     "b2llm_engine_bind_kv": (_I32, [_P, _P, _P, _U64]),

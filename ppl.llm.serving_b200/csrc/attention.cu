@@ -669,8 +669,9 @@ std::once_flag g_attn_env_once;
 
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
     (void)head_dim;
-    // rows = sequences * q heads * splits; choose_splits keeps sequences * splits <= sequences + 444
-    return (batch + 444) * num_heads * 130 * (int64_t)sizeof(float);
+    // rows = sequences * q heads * splits; choose_splits keeps sequences * splits <= sequences + 444 and the
+    // "always split" mode (split_k == 2) needs 2 per sequence
+    return (2 * batch + 444) * num_heads * 130 * (int64_t)sizeof(float);
 }
 
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end) {
@@ -743,6 +744,8 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     const int G = gq == 1 ? 1 : (gq <= 4 ? 4 : 8);
     const int chunks = (gq + G - 1) / G;
     p.nsplit = choose_splits((int64_t)p.nkv * chunks * p.decoding_batches, max_kv);
+    if (a.split_k == 0) p.nsplit = 1;
+    if (a.split_k == 2 && p.nsplit < 2 && max_kv > UNIT) p.nsplit = 2;
     // warps per CTA: one warp per CTA is fastest (no cross-warp merge, measured on B200) as long as the
     // grid alone fills the 148 x 12 warp slots; small grids get 2 or 4 warps per CTA
     const int64_t ctas = (int64_t)p.nkv * chunks * p.decoding_batches * p.nsplit;

@@ -181,6 +181,7 @@ struct AttnArgs {
     const __half* kv_scale;
     void* workspace;
     __half* out;           // [T, nq * D]
+    int split_k = 1;       // ENGINE_CONF_DECODING_ATTN_SPLIT_K: 0 off, 1 heuristic, 2 always
 };
 int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* step, int num_heads,
                               const b2llm_kv_geom& geom, int layer, const float* cos_t, const float* sin_t,

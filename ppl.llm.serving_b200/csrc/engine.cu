@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <math.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -100,6 +101,8 @@ struct b2llm_engine {
     int64_t last_tokens = 0;
     int64_t last_batch = 0;
     int attn_impl = 0, gemm_impl = 0;
+    int split_k = 1;  // B2LLM_CONF_DECODING_ATTN_SPLIT_K
+    int64_t cap_tokens = 0, cap_batch = 0;  // current capacity of the activation buffers (b2llm_engine_reserve)
     // optional per-kernel-class timing with CUDA events on the engine stream (bench.py roofline)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -248,7 +251,6 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
 
     const bool i8 = d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
     const int h = d.hidden_dim;
-    const size_t T = d.max_tokens_per_step, B = d.max_running_batch;
     int32_t rc = B2LLM_OK;
     auto chk = [&](int32_t r) { if (rc == B2LLM_OK) rc = r; };
     e->layers.resize(d.num_layers);
@@ -266,26 +268,7 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     const size_t half = e->D / 2;
     chk(e->rope_cos.ensure((size_t)d.max_position * half * 4));
     chk(e->rope_sin.ensure((size_t)d.max_position * half * 4));
-    const size_t amax_cols = (size_t)(h > e->nq * e->D ? h : e->nq * e->D);
-    chk(e->x.ensure(T * h * 2));
-    chk(e->a8.ensure(T * amax_cols));
-    chk(e->a_s.ensure(T * 4));
-    chk(e->qkv.ensure(T * e->nqkv * 2));
-    chk(e->attn.ensure(T * e->nq * e->D * 2));
-    chk(e->act.ensure(T * e->inter * 2));
-    chk(e->b8.ensure(T * e->inter));
-    chk(e->b_s.ensure(T * 4));
-    if (tp > 1) chk(e->tmp.ensure(T * h * 2));
-    if (!i8 || tp > 1) chk(e->y16.ensure(T * h * 2));
-    chk(e->xl.ensure(B * h * 2));
-    chk(e->yl.ensure(B * h * 2));
-    chk(e->logits.ensure(B * (size_t)d.vocab_size * 4));
-    chk(e->attn_ws.ensure((size_t)attention_workspace_bytes(B, e->nq, e->D)));
-    chk(e->in_tokens.ensure(T * 8));
-    chk(e->in_seq_starts.ensure((B + 1) * 8));
-    chk(e->in_kv_starts.ensure((B + 1) * 8));
-    chk(e->in_start_pos.ensure(B * 8));
-    chk(e->in_cache_idx.ensure(B * 8));
+    chk(b2llm_engine_reserve(e, d.max_tokens_per_step, d.max_running_batch));
     if (rc == B2LLM_OK) {
         std::vector<float> c((size_t)d.max_position * half), s((size_t)d.max_position * half);
         b2llm_rope_table(d.max_position, e->D, d.rope_theta, c.data(), s.data());
@@ -301,6 +284,67 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     }
     *out = e;
     return B2LLM_OK;
+}
+
+// (re)size the activation / staging buffers for steps of up to `max_tokens` tokens and `max_batch` sequences.
+// The reference gives these limits to the generator, not to the runtime (ppl.nn sizes its buffers per step),
+// so the ppl::nn::Runtime adapter calls this lazily; growth synchronises the stream first.
+extern "C" int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int64_t max_batch) {
+    B2_REQUIRE(e && max_tokens > 0 && max_batch > 0, B2LLM_ERR_INVALID_VALUE, "reserve: bad arguments");
+    if (max_tokens <= e->cap_tokens && max_batch <= e->cap_batch) return B2LLM_OK;
+    if (e->cap_tokens > 0) B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    const b2llm_model_desc& d = e->d;
+    const bool i8 = d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
+    const int h = d.hidden_dim;
+    const size_t T = (size_t)std::max<int64_t>(max_tokens, e->cap_tokens), B = (size_t)std::max<int64_t>(max_batch, e->cap_batch);
+    int32_t rc = B2LLM_OK;
+    auto chk = [&](int32_t r) { if (rc == B2LLM_OK) rc = r; };
+    const size_t amax_cols = (size_t)(h > e->nq * e->D ? h : e->nq * e->D);
+    chk(e->x.ensure(T * h * 2));
+    chk(e->a8.ensure(T * amax_cols));
+    chk(e->a_s.ensure(T * 4));
+    chk(e->qkv.ensure(T * e->nqkv * 2));
+    chk(e->attn.ensure(T * e->nq * e->D * 2));
+    chk(e->act.ensure(T * e->inter * 2));
+    chk(e->b8.ensure(T * e->inter));
+    chk(e->b_s.ensure(T * 4));
+    if (e->tp > 1) chk(e->tmp.ensure(T * h * 2));
+    if (!i8 || e->tp > 1) chk(e->y16.ensure(T * h * 2));
+    chk(e->xl.ensure(B * h * 2));
+    chk(e->yl.ensure(B * h * 2));
+    chk(e->logits.ensure(B * (size_t)d.vocab_size * 4));
+    chk(e->attn_ws.ensure((size_t)attention_workspace_bytes(B, e->nq, e->D)));
+    chk(e->in_tokens.ensure(T * 8));
+    chk(e->in_seq_starts.ensure((B + 1) * 8));
+    chk(e->in_kv_starts.ensure((B + 1) * 8));
+    chk(e->in_start_pos.ensure(B * 8));
+    chk(e->in_cache_idx.ensure(B * 8));
+    if (rc == B2LLM_OK) {
+        e->cap_tokens = (int64_t)T;
+        e->cap_batch = (int64_t)B;
+    }
+    return rc;
+}
+
+extern "C" int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t value) {
+    B2_REQUIRE(e, B2LLM_ERR_INVALID_VALUE, "configure: null engine");
+    switch (key) {
+        case B2LLM_CONF_DECODING_ATTN_SPLIT_K:
+            B2_REQUIRE(value >= 0 && value <= 2, B2LLM_ERR_INVALID_VALUE, "configure: split-k must be 0, 1 or 2");
+            e->split_k = (int)value;
+            return B2LLM_OK;
+        case B2LLM_CONF_ATTN_IMPL:
+            B2_REQUIRE(value >= 0 && value <= 2, B2LLM_ERR_INVALID_VALUE, "configure: attention impl must be 0, 1 or 2");
+            e->attn_impl = (int)value;
+            return B2LLM_OK;
+        case B2LLM_CONF_GEMM_IMPL:
+            B2_REQUIRE(value >= 0 && value <= 2, B2LLM_ERR_INVALID_VALUE, "configure: gemm impl must be 0, 1 or 2");
+            e->gemm_impl = (int)value;
+            return B2LLM_OK;
+        default:
+            set_last_error("configure: unknown key " + std::to_string(key));
+            return B2LLM_ERR_UNSUPPORTED;
+    }
 }
 
 extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
@@ -518,9 +562,9 @@ extern "C" int32_t b2llm_engine_set_inputs(b2llm_engine* e, const int64_t* token
                                            int64_t decoding_batches, int64_t max_seq_len, int64_t max_kv_len,
                                            int32_t req_list_changed) {
     B2_REQUIRE(e && token_ids && seq_starts && kv_starts && start_pos, B2LLM_ERR_INVALID_VALUE, "set_inputs: null pointer");
-    B2_REQUIRE(num_tokens >= 0 && num_tokens <= e->d.max_tokens_per_step, B2LLM_ERR_INVALID_VALUE,
+    B2_REQUIRE(num_tokens >= 0 && num_tokens <= e->cap_tokens, B2LLM_ERR_INVALID_VALUE,
                "set_inputs: num_tokens exceeds max_tokens_per_step");
-    B2_REQUIRE(batch >= 0 && batch <= e->d.max_running_batch, B2LLM_ERR_INVALID_VALUE,
+    B2_REQUIRE(batch >= 0 && batch <= e->cap_batch, B2LLM_ERR_INVALID_VALUE,
                "set_inputs: batch exceeds max_running_batch");
     cudaStream_t s = e->stream;
     B2_CHECK_CUDA(cudaMemcpyAsync(e->in_tokens.p, token_ids, num_tokens * 8, cudaMemcpyHostToDevice, s));
@@ -575,7 +619,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
     B2_REQUIRE(e->kv_cache && e->kv_scale, B2LLM_ERR_INVALID_VALUE, "forward: KV memory not bound (b2llm_engine_bind_kv)");
     const b2llm_model_desc& d = e->d;
     const int64_t T = st->num_tokens, B = st->batch;
-    B2_REQUIRE(T >= 0 && T <= d.max_tokens_per_step && B >= 0 && B <= d.max_running_batch, B2LLM_ERR_INVALID_VALUE,
+    B2_REQUIRE(T >= 0 && T <= e->cap_tokens && B >= 0 && B <= e->cap_batch, B2LLM_ERR_INVALID_VALUE,
                "forward: step exceeds max_tokens_per_step / max_running_batch");
     B2_REQUIRE(st->decoding_batches >= 0 && st->decoding_batches <= B, B2LLM_ERR_INVALID_VALUE, "forward: bad decoding_batches");
     B2_REQUIRE(st->max_kv_len <= d.max_position, B2LLM_ERR_INVALID_VALUE, "forward: max_kv_len exceeds max_position");
@@ -600,6 +644,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
     aa.kv_scale = (const __half*)e->kv_scale;
     aa.workspace = e->attn_ws.p;
     aa.out = e->attn.as<__half>();
+    aa.split_k = e->split_k;
     const int64_t decode_tokens = st->decoding_batches;  // one token per decoding sequence, placed first
     const bool tp = e->tp > 1;
     const __half* pending_skip = nullptr;  // tp > 1: all-reduced projection output not yet added to x
