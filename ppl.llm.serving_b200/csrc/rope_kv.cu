@@ -1,6 +1,6 @@
 // K4 + K5 of SURVEY.md section 2.3: rotary embedding on q,k (in place in the qkv activation) and the
 // int8 group-8 quantised append of k,v into the KV cache, for every token of the step.
-// One warp per (token, head); 16-byte accesses; group max via 4-lane shuffles.
+// Eight lanes per (token, head); 16-byte accesses; no shuffles (see the kernel comment).
 //
 // Numeric contract (oracle/llama_ref.py: apply_rope, kv_quant):
 //   rotate-half pairing (i, i + D/2); o1 = x1*c - x2*s, o2 = x2*c + x1*s with every product and sum
@@ -18,6 +18,7 @@ struct RopeKvParams {
     const int64_t* start_pos;
     const int64_t* cache_indices;
     int batch;
+    int64_t decoding_batches;
     int64_t num_tokens;
     int64_t max_pages;
     int nq, nkv, D;
@@ -29,92 +30,94 @@ struct RopeKvParams {
     KvStrides cs;    // cache strides (elements); scale strides = cs / group
 };
 
-// D = 128: lane l owns dims [4l, 4l+4) of the low half when l < 16 ... simpler: lane l owns the pair
-// columns i in {2l, 2l+1} of each half: elements (2l, 2l+1) and (D/2 + 2l, D/2 + 2l + 1).
+// 8 lanes per (token, head): lane j owns the 16-byte chunk j of the low half (dims [8j, 8j+8)) and the matching
+// chunk of the high half (dims [D/2 + 8j, D/2 + 8j + 8)) -- exactly the rotate-half partners, and exactly one
+// quantisation group each, so neither the rotation nor the group max needs a shuffle.  D = 128 uses all 8 lanes
+// of the sub-group, D = 64 the first 4.  A warp covers 4 heads of one token.
 template <int D>
-__global__ void __launch_bounds__(128) rope_kv_append_kernel(RopeKvParams p) {
+__global__ void __launch_bounds__(256) rope_kv_append_kernel(RopeKvParams p) {
     constexpr int HALF = D / 2;
-    constexpr int PER = HALF / 32;  // pair-columns per lane (2 for D = 128, 1 for D = 64)
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int CHUNKS = HALF / 8;  // 16-byte chunks per half: 8 (D = 128) or 4 (D = 64)
+    const int sub = threadIdx.x & 7;
     const int heads = p.nq + 2 * p.nkv;
-    if (w >= p.num_tokens * heads) return;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // (token, head) index
+    if (w >= p.num_tokens * heads || sub >= CHUNKS) return;
     const int64_t t = w / heads;
-    const int h = (int)(w % heads);
-    const int b = find_seq(p.seq_starts, p.batch, t);
+    const int h = (int)(w - t * heads);
+    // decode sequences come first with one token each (llm_generator.cc:229-242): token t < decoding_batches
+    // belongs to sequence t; prefill tokens need the search
+    const int b = t < p.decoding_batches ? (int)t : find_seq(p.seq_starts, p.batch, t);
     const int64_t pos = p.start_pos[b] + (t - p.seq_starts[b]);
 
-    __half* row = p.qkv + t * (int64_t)heads * D + (int64_t)h * D;
-    float lo[PER], hi[PER];
-    if constexpr (PER == 2) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(row + 2 * lane));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(row + HALF + 2 * lane));
-        lo[0] = a.x; lo[1] = a.y; hi[0] = c.x; hi[1] = c.y;
-    } else {
-        lo[0] = __half2float(row[lane]);
-        hi[0] = __half2float(row[HALF + lane]);
+    __half* row = p.qkv + (t * heads + h) * (int64_t)D;
+    const uint4 ulo = *reinterpret_cast<const uint4*>(row + 8 * sub);
+    const uint4 uhi = *reinterpret_cast<const uint4*>(row + HALF + 8 * sub);
+    float lo[8], hi[8];
+    {
+        const __half2* a = reinterpret_cast<const __half2*>(&ulo);
+        const __half2* c = reinterpret_cast<const __half2*>(&uhi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = __half22float2(a[i]), fc = __half22float2(c[i]);
+            lo[2 * i] = fa.x; lo[2 * i + 1] = fa.y; hi[2 * i] = fc.x; hi[2 * i + 1] = fc.y;
+        }
     }
 
     const bool is_v = h >= p.nq + p.nkv;
     if (!is_v) {
+        const float4* cp = reinterpret_cast<const float4*>(p.cos_t + pos * HALF + 8 * sub);
+        const float4* sp = reinterpret_cast<const float4*>(p.sin_t + pos * HALF + 8 * sub);
+        const float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int col = PER * lane + i;
-            const float c = p.cos_t[pos * HALF + col], s = p.sin_t[pos * HALF + col];
-            const float o1 = __fsub_rn(__fmul_rn(lo[i], c), __fmul_rn(hi[i], s));
-            const float o2 = __fadd_rn(__fmul_rn(hi[i], c), __fmul_rn(lo[i], s));
+        for (int i = 0; i < 8; ++i) {
+            const float o1 = __fsub_rn(__fmul_rn(lo[i], cs[i]), __fmul_rn(hi[i], sn[i]));
+            const float o2 = __fadd_rn(__fmul_rn(hi[i], cs[i]), __fmul_rn(lo[i], sn[i]));
             lo[i] = __half2float(__float2half_rn(o1));
             hi[i] = __half2float(__float2half_rn(o2));
         }
-        if constexpr (PER == 2) {
-            *reinterpret_cast<__half2*>(row + 2 * lane) = __floats2half2_rn(lo[0], lo[1]);
-            *reinterpret_cast<__half2*>(row + HALF + 2 * lane) = __floats2half2_rn(hi[0], hi[1]);
-        } else {
-            row[lane] = __float2half_rn(lo[0]);
-            row[HALF + lane] = __float2half_rn(hi[0]);
+        uint4 olo, ohi;
+        __half2* a = reinterpret_cast<__half2*>(&olo);
+        __half2* c = reinterpret_cast<__half2*>(&ohi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = __floats2half2_rn(lo[2 * i], lo[2 * i + 1]);
+            c[i] = __floats2half2_rn(hi[2 * i], hi[2 * i + 1]);
         }
+        *reinterpret_cast<uint4*>(row + 8 * sub) = olo;
+        *reinterpret_cast<uint4*>(row + HALF + 8 * sub) = ohi;
     }
     if (h < p.nq) return;
 
-    // ---- quantised append.  group of 8 dims = 8 / PER consecutive lanes in each half.
+    // ---- quantised append: this lane's two chunks are two whole quantisation groups
     const int kv = is_v ? 1 : 0;
     const int hk = h - p.nq - kv * p.nkv;
     const int64_t slot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
-    int8_t* crow = p.cache + kv * p.cs.kv + hk * p.cs.head + slot * p.cs.tok;
-    __half* srow = p.scale + (kv * p.cs.kv + hk * p.cs.head + slot * p.cs.tok) / p.group;
+    const int64_t off = kv * p.cs.kv + hk * p.cs.head + slot * p.cs.tok;
+    int8_t* crow = p.cache + off;
+    __half* srow = p.scale + off / 8;
 
     float mlo = 0.f, mhi = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
+    for (int i = 0; i < 8; ++i) {
         mlo = fmaxf(mlo, fabsf(lo[i]));
         mhi = fmaxf(mhi, fabsf(hi[i]));
     }
-    constexpr int LANES_PER_GROUP = 8 / PER;
-#pragma unroll
-    for (int o = 1; o < LANES_PER_GROUP; o <<= 1) {
-        mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-        mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
-    }
     const __half slo16 = __float2half_rn(__fdiv_rn(mlo, 127.0f)), shi16 = __float2half_rn(__fdiv_rn(mhi, 127.0f));
     const float slo = __half2float(slo16), shi = __half2float(shi16);
-    int qlo[PER], qhi[PER];
+    uint32_t wlo[2] = {0u, 0u}, whi[2] = {0u, 0u};
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        qlo[i] = slo > 0.f ? max(-127, min(127, __float2int_rn(__fdiv_rn(lo[i], slo)))) : 0;
-        qhi[i] = shi > 0.f ? max(-127, min(127, __float2int_rn(__fdiv_rn(hi[i], shi)))) : 0;
+    for (int i = 0; i < 8; ++i) {
+        const int ql = slo > 0.f ? max(-127, min(127, __float2int_rn(__fdiv_rn(lo[i], slo)))) : 0;
+        const int qh = shi > 0.f ? max(-127, min(127, __float2int_rn(__fdiv_rn(hi[i], shi)))) : 0;
+        wlo[i >> 2] |= (uint32_t)(ql & 0xff) << (8 * (i & 3));
+        whi[i >> 2] |= (uint32_t)(qh & 0xff) << (8 * (i & 3));
     }
-    if constexpr (PER == 2) {
-        *reinterpret_cast<uint16_t*>(crow + 2 * lane) = (uint16_t)((qlo[0] & 0xff) | ((qlo[1] & 0xff) << 8));
-        *reinterpret_cast<uint16_t*>(crow + HALF + 2 * lane) = (uint16_t)((qhi[0] & 0xff) | ((qhi[1] & 0xff) << 8));
-    } else {
-        crow[lane] = (int8_t)qlo[0];
-        crow[HALF + lane] = (int8_t)qhi[0];
-    }
-    if ((lane % LANES_PER_GROUP) == 0) {
-        const int gidx = lane / LANES_PER_GROUP;  // group index inside the half
-        srow[gidx] = slo16;
-        srow[HALF / 8 + gidx] = shi16;
-    }
+    *reinterpret_cast<uint2*>(crow + 8 * sub) = make_uint2(wlo[0], wlo[1]);
+    *reinterpret_cast<uint2*>(crow + HALF + 8 * sub) = make_uint2(whi[0], whi[1]);
+    srow[sub] = slo16;
+    srow[CHUNKS + sub] = shi16;
 }
 
 }  // namespace
@@ -132,6 +135,7 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
     p.cache_indices = step->cache_indices;
     p.batch = (int)step->batch;
     p.num_tokens = step->num_tokens;
+    p.decoding_batches = step->decoding_batches;
     p.max_pages = step->max_pages;
     p.nq = num_heads;
     p.nkv = geom.num_kv_heads;
@@ -144,12 +148,12 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
     p.cs = kv_strides(geom);
     p.cache = kv_cache + (int64_t)layer * p.cs.layer;
     p.scale = kv_scale + (int64_t)layer * p.cs.layer / geom.quant_group;
-    const int64_t warps = step->num_tokens * (num_heads + 2 * geom.num_kv_heads);
-    const unsigned blocks = (unsigned)((warps + 3) / 4);
+    const int64_t threads = step->num_tokens * (num_heads + 2 * geom.num_kv_heads) * 8;
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
     if (geom.head_dim == 128)
-        rope_kv_append_kernel<128><<<blocks, 128, 0, s>>>(p);
+        rope_kv_append_kernel<128><<<blocks, 256, 0, s>>>(p);
     else
-        rope_kv_append_kernel<64><<<blocks, 128, 0, s>>>(p);
+        rope_kv_append_kernel<64><<<blocks, 256, 0, s>>>(p);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
