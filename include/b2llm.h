@@ -221,7 +221,8 @@ B2LLM_API int32_t b2llm_op_quant_rows(void* stream, const void* x_fp16, int64_t 
 /* W8A8 GEMM: C[m, n] = epilogue((int32) sum_k A[m,k] * W[n,k], a_scale[m], w_scale[n]).
  * epilogue: 0 -> fp16 out [M, N]; 1 -> out = fp16(out + value) (residual add, in place);
  *           2 -> SwiGLU over interleaved (gate, up) column pairs -> fp16 out [M, N/2];
- * impl: 0 auto, 1 mma.sync baseline, 2 tcgen05 */
+ * impl: 0 auto, 1 mma.sync baseline, 2 tcgen05 single-CTA kernel, 3 tcgen05 CTA-pair kernel (cta_group::2;
+ *       falls back to the single-CTA kernel when M <= 128 or N % 256 != 0) */
 B2LLM_API int32_t b2llm_op_gemm_w8a8(void* stream, const int8_t* a, const float* a_scale, const int8_t* w,
                                      const float* w_scale, int64_t M, int32_t N, int32_t K, int32_t epilogue,
                                      void* out_fp16, int32_t impl);

@@ -240,11 +240,49 @@ def _attend(q, K, V, last_visible):
 
 # --------------------------------------------------------------------------- the step
 class LlamaOracle:
-    def __init__(self, desc: ModelDesc, weights: SynthWeights, kv_max_tokens: int):
+    """``tp`` > 1 restates the reference's tensor parallelism (``--tensor-parallel-size``; one model slice per rank,
+    ``resource_manager.cc:280-286``; ``num_kv_heads / tp`` per rank, ``llm_engine.cc:124``): q/k/v/gate/up are split
+    by output channel (results identical to tp = 1: per-channel weight scales, same quantised input), o_proj and
+    down_proj by input channel -- each rank quantises ITS slice of the activation row and ITS slice of the weight
+    (scale = slice max / 127), stores its partial product as fp16 and the partials are summed (the all-reduce at the
+    "two residual join points").  ``allreduce``: None = simulate all ranks in this process; otherwise a callable
+    ``fp16 [T, h] partial of `rank` -> fp16 sum over ranks`` (tests/test_tp_gloo.py runs one process per rank)."""
+
+    def __init__(self, desc: ModelDesc, weights: SynthWeights, kv_max_tokens: int, tp: int = 1, rank: int | None = None,
+                 allreduce=None):
         self.desc = desc
         self.w = weights
         self.cache = KVCache(desc, kv_max_tokens)
         self.cos, self.sin = rope_table(desc.max_position, desc.head_dim, desc.rope_theta)
+        self.tp, self.rank, self.allreduce = tp, rank, allreduce
+        self._slice_cache = {}
+
+    def _row_parallel_partial(self, r: int, x16: np.ndarray, lw, name: str, layer: int) -> np.ndarray:
+        """rank r's fp16 partial of a row-parallel projection: columns [r*K/tp, (r+1)*K/tp) of x and W"""
+        d = self.desc
+        K = x16.shape[1]
+        lo, hi = r * K // self.tp, (r + 1) * K // self.tp
+        xs = x16[:, lo:hi]
+        if d.quant_method == 1:
+            key = (layer, name, r)
+            if key not in self._slice_cache:
+                from .weights import quantize_weight_per_channel
+                self._slice_cache[key] = quantize_weight_per_channel(lw[name][:, lo:hi])
+            wq, ws = self._slice_cache[key]
+            q, s = quant_rows(xs.astype(F32))
+            return dequant_acc(gemm_i8_acc(q, wq), s, ws).astype(np.float16)
+        return gemm_f16_acc(xs, lw[name][:, lo:hi]).astype(np.float16)
+
+    def _row_parallel(self, x16: np.ndarray, lw, name: str, layer: int) -> np.ndarray:
+        """fp32 [T, h]: the projection output that is added to the residual stream"""
+        if self.tp == 1:
+            return self._linear(x16.astype(F32) if self.desc.quant_method == 1 else x16, lw, name)
+        if self.allreduce is not None:
+            return self.allreduce(self._row_parallel_partial(self.rank, x16, lw, name, layer)).astype(F32)
+        total = np.zeros((x16.shape[0], lw[name].shape[0]), dtype=F32)
+        for r in range(self.tp):
+            total += self._row_parallel_partial(r, x16, lw, name, layer).astype(F32)
+        return total.astype(np.float16).astype(F32)
 
     # linear layer in the model's quant mode: returns fp32 pre-rounding result
     def _linear(self, x_f32_or_16, lw, name, prequant=None):
@@ -321,7 +359,7 @@ class LlamaOracle:
                 attn16[r, j] = np.nextafter(attn16[r, j], np.float16(0))
             if trace is not None and l == 0:
                 trace["l0_attn"] = attn16.copy()
-            o = self._linear(attn16.astype(F32) if d.quant_method == 1 else attn16, lw, "wo")
+            o = self._row_parallel(attn16, lw, "wo", l)
             x = (x.astype(F32) + o).astype(np.float16)
             if trace is not None and l == 0:
                 trace["l0_x_mid"] = x.copy()
@@ -339,7 +377,7 @@ class LlamaOracle:
             act = silu_mul(g, u).astype(np.float16)
             if trace is not None and l == 0:
                 trace["l0_act"] = act.copy()
-            dn = self._linear(act.astype(F32) if d.quant_method == 1 else act, lw, "wdown")
+            dn = self._row_parallel(act, lw, "wdown", l)
             x = (x.astype(F32) + dn).astype(np.float16)
             if trace is not None and l == 0:
                 trace["l0_x_out"] = x.copy()

@@ -168,7 +168,8 @@ int32_t launch_gather_rows(cudaStream_t s, const __half* x, const int64_t* seq_s
 int32_t launch_gemm_mma(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w,
                         const float* w_scale, int64_t M, int N, int K, int epilogue, void* out, int64_t ldc);
 int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w,
-                       const float* w_scale, int64_t M, int N, int K, int epilogue, void* out, int64_t ldc);
+                       const float* w_scale, int64_t M, int N, int K, int epilogue, void* out, int64_t ldc,
+                       int pair_mode = -1);  // -1 default (B2LLM_GEMM_2CTA), 0 single-CTA kernel, 2 CTA-pair kernel
 bool gemm_tc_available();
 
 struct AttnArgs {

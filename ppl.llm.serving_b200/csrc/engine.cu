@@ -814,9 +814,10 @@ extern "C" int32_t b2llm_op_gemm_w8a8(void* stream, const int8_t* a, const float
     B2_REQUIRE(a && a_scale && w && w_scale && out_fp16, B2LLM_ERR_INVALID_VALUE, "gemm_w8a8: null pointer");
     B2_REQUIRE(epilogue >= 0 && epilogue <= 2, B2LLM_ERR_INVALID_VALUE, "gemm_w8a8: epilogue must be 0, 1 or 2");
     const int64_t ldc = epilogue == EPI_SWIGLU ? N / 2 : N;
-    if (impl == 2 || (impl == 0 && gemm_tc_available())) {
-        const int32_t rc = launch_gemm_tc((cudaStream_t)stream, true, a, a_scale, w, w_scale, M, N, K, epilogue, out_fp16, ldc);
-        if (rc != B2LLM_ERR_UNSUPPORTED || impl == 2) return rc;
+    if (impl >= 2 || (impl == 0 && gemm_tc_available())) {
+        const int32_t rc = launch_gemm_tc((cudaStream_t)stream, true, a, a_scale, w, w_scale, M, N, K, epilogue, out_fp16, ldc,
+                                          impl == 2 ? 0 : (impl == 3 ? 2 : -1));
+        if (rc != B2LLM_ERR_UNSUPPORTED || impl >= 2) return rc;
     }
     return launch_gemm_mma((cudaStream_t)stream, true, a, a_scale, w, w_scale, M, N, K, epilogue, out_fp16, ldc);
 }
@@ -826,9 +827,10 @@ extern "C" int32_t b2llm_op_gemm_f16(void* stream, const void* a_fp16, const voi
     B2_REQUIRE(a_fp16 && w_fp16 && out, B2LLM_ERR_INVALID_VALUE, "gemm_f16: null pointer");
     B2_REQUIRE(epilogue >= 0 && epilogue <= 3, B2LLM_ERR_INVALID_VALUE, "gemm_f16: epilogue must be 0..3");
     if (ldc <= 0) ldc = epilogue == EPI_SWIGLU ? N / 2 : N;
-    if (impl == 2 || (impl == 0 && gemm_tc_available())) {
-        const int32_t rc = launch_gemm_tc((cudaStream_t)stream, false, a_fp16, nullptr, w_fp16, nullptr, M, N, K, epilogue, out, ldc);
-        if (rc != B2LLM_ERR_UNSUPPORTED || impl == 2) return rc;
+    if (impl >= 2 || (impl == 0 && gemm_tc_available())) {
+        const int32_t rc = launch_gemm_tc((cudaStream_t)stream, false, a_fp16, nullptr, w_fp16, nullptr, M, N, K, epilogue, out, ldc,
+                                          impl == 2 ? 0 : (impl == 3 ? 2 : -1));
+        if (rc != B2LLM_ERR_UNSUPPORTED || impl >= 2) return rc;
     }
     return launch_gemm_mma((cudaStream_t)stream, false, a_fp16, nullptr, w_fp16, nullptr, M, N, K, epilogue, out, ldc);
 }

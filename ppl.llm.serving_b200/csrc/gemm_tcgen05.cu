@@ -99,6 +99,64 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
     return d;
 }
 
+// one epilogue chunk: 32 consecutive output columns [n0, n0 + 32) of row m, straight from the accumulator
+template <bool I8, int EPI>
+__device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], int m, int n0, float sa_m,
+                                                 const float* __restrict__ w_scale, void* __restrict__ out, int64_t ldc) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if constexpr (I8)
+            v[i] = dequant((int)r[i], sa_m, __ldg(w_scale + n0 + i));
+        else
+            v[i] = __uint_as_float(r[i]);
+    }
+    if constexpr (EPI == EPI_F16 || EPI == EPI_RESIDUAL) {
+        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + n0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+            if constexpr (EPI == EPI_RESIDUAL) {
+                const uint4 old = *reinterpret_cast<const uint4*>(orow + q * 8);
+                const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ow[j]));
+                    __half2 h = __floats2half2_rn(__fadd_rn(o2.x, v[q * 8 + 2 * j]), __fadd_rn(o2.y, v[q * 8 + 2 * j + 1]));
+                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half2 h = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            }
+            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
+        }
+    } else if constexpr (EPI == EPI_SWIGLU) {
+        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + (n0 >> 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = q * 16 + 4 * j;
+                __half2 h = __floats2half2_rn(silu_mul_f32(v[i], v[i + 1]), silu_mul_f32(v[i + 2], v[i + 3]));
+                pw[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
+        }
+    } else {
+        float* orow = reinterpret_cast<float*>(out) + (int64_t)m * ldc + n0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(orow + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
 template <bool I8, int EPI, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -203,60 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 if (n0 >= N) break;  // warp-uniform
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
-                if (m < M) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if constexpr (I8)
-                            v[i] = dequant((int)r[i], sa_m, __ldg(w_scale + n0 + i));
-                        else
-                            v[i] = __uint_as_float(r[i]);
-                    }
-                    if constexpr (EPI == EPI_F16 || EPI == EPI_RESIDUAL) {
-                        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + n0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 pk;
-                            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-                            if constexpr (EPI == EPI_RESIDUAL) {
-                                const uint4 old = *reinterpret_cast<const uint4*>(orow + q * 8);
-                                const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ow[j]));
-                                    __half2 h = __floats2half2_rn(__fadd_rn(o2.x, v[q * 8 + 2 * j]), __fadd_rn(o2.y, v[q * 8 + 2 * j + 1]));
-                                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    __half2 h = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-                                    pw[j] = *reinterpret_cast<uint32_t*>(&h);
-                                }
-                            }
-                            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
-                        }
-                    } else if constexpr (EPI == EPI_SWIGLU) {
-                        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + (n0 >> 1);
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            uint4 pk;
-                            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int i = q * 16 + 4 * j;
-                                __half2 h = __floats2half2_rn(silu_mul_f32(v[i], v[i + 1]), silu_mul_f32(v[i + 2], v[i + 3]));
-                                pw[j] = *reinterpret_cast<uint32_t*>(&h);
-                            }
-                            *reinterpret_cast<uint4*>(orow + q * 8) = pk;
-                        }
-                    } else {
-                        float* orow = reinterpret_cast<float*>(out) + (int64_t)m * ldc + n0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(orow + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                }
+                if (m < M) epilogue_store32<I8, EPI>(r, m, n0, sa_m, w_scale, out, ldc);
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
@@ -268,6 +273,207 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- CTA-pair kernel (tcgen05 cta_group::2)
+// The 1-CTA kernel above is bounded by L2 -> shared-memory traffic, not by the tensor pipe: a 128 x 256 tile
+// needs 48 KB per 128-byte k-block, ~12 TB/s at the rate the pipe could consume it (profiles/r1_ncu_gemm.txt:
+// tensor pipe 47-49 % active).  A CTA pair computes a 256 x 256 tile with ONE UMMA of M = 256: each CTA stages
+// its own 128 rows of A and only HALF of the weight tile (128 of the 256 output channels), the pair's tensor
+// cores read both halves -- 32 KB per CTA per k-block for the same math, i.e. 2/3 of the traffic, and a six-
+// instead of four-stage ring in the same shared memory.
+//   * cluster (2,1,1); rank 0 = leader.  Both CTAs run the TMA producer (their own A rows / W half) with
+//     cp.async.bulk.tensor ... .cta_group::2 completing on the LEADER's full barrier (mapa address);
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256, N = 256); tcgen05.commit ... multicast 0b11
+//     releases the smem stage in both CTAs / publishes the accumulator to both epilogues;
+//   * each CTA's epilogue drains its own TMEM (its 128 rows); both arrive on the leader's tempty barrier
+//     (the peer through a remote mbarrier.arrive).
+constexpr int BN2 = 256;
+struct Cfg2 {
+    static constexpr int STAGES = 6;
+    static constexpr int A_BYTES = BM * BKB;                 // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_BYTES = (BN2 / 2) * BKB;          // 16 KB: this CTA's half of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB
+    static constexpr int TMEM_COLS = 2 * BN2;                // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// dst: this CTA's shared memory; bar: an mbarrier of either CTA of the pair (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <bool I8>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    if constexpr (I8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+    }
+}
+
+template <bool I8>
+__host__ __device__ constexpr uint32_t make_idesc_pair() {
+    uint32_t d = 0;
+    d |= (I8 ? 2u : 1u) << 4;
+    d |= (I8 ? 1u : 0u) << 7;
+    d |= (I8 ? 1u : 0u) << 10;
+    d |= (uint32_t)(BN2 >> 3) << 17;       // N = 256
+    d |= (uint32_t)((2 * BM) >> 4) << 24;  // M = 256 across the pair
+    return d;
+}
+
+template <bool I8, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const float* __restrict__ a_scale, const float* __restrict__ w_scale, int M, int N, int Kb,
+                    void* __restrict__ out, int64_t ldc) {
+    using C = Cfg2;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };                          // leader's is used
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };           // per CTA
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };       // per CTA
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };  // leader's is used
+    const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM), num_n = N / BN2;
+    const int num_tiles = num_m * num_n;
+    const int nk = Kb / BKB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 256);  // 128 epilogue threads of each CTA
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything crosses
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_w);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                const int row_a = m_blk * 2 * BM + (int)rank * BM;
+                const int row_w = n_blk * BN2 + (int)rank * (BN2 / 2);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    const uint32_t fb = mapa_u32(full_bar(stage), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);  // both CTAs' bytes
+                    tma_load_2d_pair(sa, &map_a, fb, kb * BKB, row_a);
+                    tma_load_2d_pair(sb, &map_w, fb, kb * BKB, row_w);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_pair<I8>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * BN2;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BKB / 32; ++k)
+                        tc_mma_pair<I8>(tmem_c, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_pair(empty_bar(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(tfull_bar(acc));
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int m = m_blk * 2 * BM + (int)rank * BM + quarter * 32 + lane;
+            const float sa_m = (I8 && m < M) ? a_scale[m] : 1.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
+#pragma unroll 1
+            for (int c = 0; c < BN2 / 32; ++c) {
+                const int n0 = n_blk * BN2 + c * 32;
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                if (m < M) epilogue_store32<I8, EPI>(r, m, n0, sa_m, w_scale, out, ldc);
+            }
+            tc_fence_before();
+            if (rank == 0) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_remote(acc ? tempty_leader1 : tempty_leader0);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair may still signal / read it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
     }
 }
 
@@ -318,8 +524,32 @@ int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* 
 }
 
 template <bool I8, int EPI>
+int32_t launch_pair(cudaStream_t s, const void* a, const float* a_scale, const void* w, const float* w_scale, int64_t M, int N,
+                    int Kb, void* out, int64_t ldc) {
+    using C = Cfg2;
+    auto kern = gemm_tc2_kernel<I8, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    CUtensorMap ma, mw;
+    B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)Kb, BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
+    B2_REQUIRE(cached_map(&mw, w, (uint64_t)N, (uint64_t)Kb, BN2 / 2), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W) failed");
+    const int tiles = (int)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
+    const int max_pairs = device_num_sms() / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    kern<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int g_gemm_pair_mode = -1;  // B2LLM_GEMM_2CTA: 0 never, 1 auto (default), 2 whenever the shape allows
+std::once_flag g_gemm_env_once;
+
+template <bool I8, int EPI>
 int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void* w, const float* w_scale, int64_t M, int N,
-                int Kb, void* out, int64_t ldc) {
+                int Kb, void* out, int64_t ldc, int pair_mode) {
     // wave efficiency of the persistent schedule for both tile widths
     auto eff = [&](int bn) {
         const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
@@ -328,6 +558,15 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
         const double useful = (double)M * N / ((double)((M + BM - 1) / BM * BM) * ((N + bn - 1) / bn * bn));
         return useful * (double)tiles / (double)(rounds * g_num_sms);
     };
+    std::call_once(g_gemm_env_once, [] {
+        const char* e = getenv("B2LLM_GEMM_2CTA");
+        g_gemm_pair_mode = e ? atoi(e) : 1;
+    });
+    // CTA pairs: 256 x 256 tiles.  Worth it once there are at least two 128-row blocks of A to pair up.
+    const bool pair_ok = N % BN2 == 0 && M > BM;
+    const int mode = pair_mode >= 0 ? pair_mode : g_gemm_pair_mode;
+    if (pair_ok && (mode == 2 || (mode == 1 && M >= 2 * BM)))
+        return launch_pair<I8, EPI>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
     if (N >= 256 && eff(256) >= eff(128) * 0.97)
         return launch<I8, EPI, 256>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
     return launch<I8, EPI, 128>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
@@ -338,7 +577,7 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
 bool gemm_tc_available() { return tma_available(); }
 
 int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w, const float* w_scale,
-                       int64_t M, int N, int K, int epilogue, void* out, int64_t ldc) {
+                       int64_t M, int N, int K, int epilogue, void* out, int64_t ldc, int pair_mode) {
     if (!gemm_tc_available()) {
         set_last_error("tcgen05 gemm: needs an sm_100 device and cuTensorMapEncodeTiled");
         return B2LLM_ERR_UNSUPPORTED;
@@ -353,17 +592,17 @@ int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a
     if (M == 0) return B2LLM_OK;
     if (is_i8) {
         switch (epilogue) {
-            case EPI_F16: return pick_bn<true, EPI_F16>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
-            case EPI_RESIDUAL: return pick_bn<true, EPI_RESIDUAL>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
-            case EPI_SWIGLU: return pick_bn<true, EPI_SWIGLU>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
+            case EPI_F16: return pick_bn<true, EPI_F16>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc, pair_mode);
+            case EPI_RESIDUAL: return pick_bn<true, EPI_RESIDUAL>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc, pair_mode);
+            case EPI_SWIGLU: return pick_bn<true, EPI_SWIGLU>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc, pair_mode);
             default: break;
         }
     } else {
         switch (epilogue) {
-            case EPI_F16: return pick_bn<false, EPI_F16>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
-            case EPI_RESIDUAL: return pick_bn<false, EPI_RESIDUAL>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
-            case EPI_SWIGLU: return pick_bn<false, EPI_SWIGLU>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
-            case EPI_F32: return pick_bn<false, EPI_F32>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc);
+            case EPI_F16: return pick_bn<false, EPI_F16>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc, pair_mode);
+            case EPI_RESIDUAL: return pick_bn<false, EPI_RESIDUAL>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc, pair_mode);
+            case EPI_SWIGLU: return pick_bn<false, EPI_SWIGLU>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc, pair_mode);
+            case EPI_F32: return pick_bn<false, EPI_F32>(s, a, nullptr, w, nullptr, M, N, Kb, out, ldc, pair_mode);
             default: break;
         }
     }

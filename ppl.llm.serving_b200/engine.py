@@ -239,14 +239,19 @@ class CudaResourceManager:
 
     def Init(self, model_desc, max_tokens_scale: float, max_running_batch: int, max_tokens_per_step: int,
              enable_penalty: bool = False, kv_cache_max_tokens: int | None = None, seed: int | None = 0xB200,
-             device: int = 0) -> int:
+             device: int = 0, tensor_parallel_size: int = 1, rank: int = 0, nccl_comm=None) -> int:
+        """``tensor_parallel_size`` > 1: this process is rank ``rank`` of a TP group (one process per GPU) and
+        ``nccl_comm`` its raw ncclComm_t (nccl.create_comm); every rank must use the same ``kv_cache_max_tokens``
+        (the reference takes rank 0's number for all, resource_manager.cc:329-344)."""
         torch.cuda.set_device(device)
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
         self.desc = model_desc
+        self.tp, self.rank = tensor_parallel_size, rank
         dc = capi.desc_to_c(model_desc, max_tokens_per_step, max_running_batch)
         eng = C.c_void_p()
-        rc = self.lib.b2llm_engine_create(C.byref(dc), 0, 1, None, C.c_void_p(self.stream.cuda_stream), C.byref(eng))
+        rc = self.lib.b2llm_engine_create(C.byref(dc), rank, tensor_parallel_size, nccl_comm,
+                                          C.c_void_p(self.stream.cuda_stream), C.byref(eng))
         if rc != RC_SUCCESS:
             return rc
         self.engine = eng
@@ -266,6 +271,11 @@ class CudaResourceManager:
             f = np.float32(max_tokens_scale) * np.float32(free)
             f = np.float32(np.float32(f * np.float32(cb)) / np.float32(cb + sb))
             kv_cache_max_tokens = int(np.uint64(f)) // cb
+            if tensor_parallel_size > 1:  # all ranks use rank 0's budget (resource_manager.cc:329-344)
+                import torch.distributed as dist
+                t = torch.tensor([kv_cache_max_tokens], dtype=torch.int64, device="cuda")
+                dist.broadcast(t, src=0)
+                kv_cache_max_tokens = int(t.item())
         self.kv_cache_max_tokens = int(kv_cache_max_tokens)
         self.kv_cache_mem = torch.empty(self.kv_cache_max_tokens * cb, dtype=torch.int8, device="cuda")
         self.kv_scale_mem = torch.empty(self.kv_cache_max_tokens * sb // 2, dtype=torch.float16, device="cuda")

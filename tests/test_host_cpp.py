@@ -159,3 +159,39 @@ def test_reference_offline_inference_tool_runs(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     assert "generation time:" in r.stdout
     assert r.stderr.count("Prompt: ") == 4 and "Answer:" in r.stderr
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_generator_tensor_parallel_2(tmp_path):
+    """--tensor-parallel-size 2 through the reference's own single-process bring-up: InitNccl (one comm per GPU),
+    one device-worker thread per rank, ParallelExecute fork/join twice per step."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    desc = ModelDesc(512, 1024, 2, 4, 2, 1024, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=256)
+    weights = SynthWeights(desc, 0xB200)
+    mdir = write_model_dir(tmp_path / "model", desc, tensor_parallel_size=2, seed=0xB200)
+    rng = np.random.default_rng(23)
+    reqs = [(i, 5, list(map(int, rng.integers(0, desc.vocab_size, n)))) for i, n in enumerate((6, 21, 11))]
+    (tmp_path / "req.txt").write_text("".join(f"{i} {g} {' '.join(map(str, p))}\n" for i, g, p in reqs))
+    r = _run([DRIVER, "--model-dir", mdir, "--tensor-parallel-size", 2, "--requests-file", tmp_path / "req.txt",
+              "--out", tmp_path / "out.txt", "--max-running-batch", 8, "--max-tokens-per-step", 256,
+              "--max-tokens-scale", 0.01])
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = {int(l.split()[0]): list(map(int, l.split()[1:])) for l in (tmp_path / "out.txt").read_text().splitlines()}
+    for i, g, p in reqs:
+        pages = (len(p) + g + 15) // 16
+        orc = ref.LlamaOracle(desc, weights, pages * 16, tp=2)
+        kw = dict(page_tables=[[k * 16 for k in range(pages)]])
+        step = ref.build_step(desc, [p], [0], 0, **kw)
+        pos = len(p)
+        for k in range(g):
+            logits = orc.forward(step)
+            t = int(logits[0].argmax())
+            top2 = np.sort(logits[0])[-2:]
+            if got[i][k] != t:
+                assert (top2[1] - top2[0]) / np.abs(logits[0]).max() < 2e-3, (i, k, got[i], t)
+                break
+            step = ref.build_step(desc, [[t]], [pos], 1, **kw)
+            pos += 1

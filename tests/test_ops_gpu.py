@@ -124,16 +124,17 @@ def _gemm_inputs(M, N, K, seed):
     return a, w, sa, sw
 
 
-@pytest.mark.parametrize("impl", [1, 2])
-@pytest.mark.parametrize("M,N,K", [(1, 128, 64), (17, 384, 256), (128, 256, 4096), (300, 1280, 1024), (1024, 512, 11008)])
+@pytest.mark.parametrize("impl", [1, 2, 3])  # 3 = CTA-pair kernel (cta_group::2) where the shape allows it
+@pytest.mark.parametrize("M,N,K", [(1, 128, 64), (17, 384, 256), (128, 256, 4096), (300, 1280, 1024), (1024, 512, 11008),
+                                   (513, 768, 256), (1024, 4096, 4096), (2048, 22016, 512)])
 def test_gemm_w8a8_f16_bit_exact(lib, impl, M, N, K):
-    if impl == 2 and not _tc_ok(lib):
+    if impl >= 2 and not _tc_ok(lib):
         pytest.skip("tcgen05 path not built")
     a, w, sa, sw = _gemm_inputs(M, N, K, M + N + K)
     out = torch.zeros((M, N), dtype=torch.float16, device="cuda")
     rc = lib.b2llm_op_gemm_w8a8(stream_ptr(), _ptr(dev(a)), _ptr(dev(sa)), _ptr(dev(w)), _ptr(dev(sw)), M, N, K,
                                 capi.EPI_F16, _ptr(out), impl)
-    if impl == 2 and rc == 4 and K % 128 != 0:
+    if impl >= 2 and rc == 4 and K % 128 != 0:
         pytest.skip("K outside the tcgen05 kernel's envelope (falls back to the mma.sync kernel when impl = 0)")
     capi.check(rc, "gemm")
     sync()
@@ -150,11 +151,11 @@ def _tc_ok(lib):
     return rc == 0
 
 
-@pytest.mark.parametrize("impl", [1, 2])
-def test_gemm_w8a8_residual_and_swiglu(lib, impl):
-    if impl == 2 and not _tc_ok(lib):
+@pytest.mark.parametrize("impl,M", [(1, 67), (2, 67), (2, 400), (3, 400), (3, 1024)])
+def test_gemm_w8a8_residual_and_swiglu(lib, impl, M):
+    if impl >= 2 and not _tc_ok(lib):
         pytest.skip("tcgen05 path not built")
-    M, N, K = 67, 512, 512
+    N, K = 512, 512
     a, w, sa, sw = _gemm_inputs(M, N, K, 9)
     rng = np.random.default_rng(1)
     res = rng.standard_normal((M, N)).astype(np.float16)
@@ -175,15 +176,15 @@ def test_gemm_w8a8_residual_and_swiglu(lib, impl):
     np.testing.assert_allclose(out2.cpu().numpy().astype(np.float32), exp2, rtol=2e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
-@pytest.mark.parametrize("M,N,K", [(3, 256, 128), (130, 1024, 512), (64, 32000, 4096)])
+@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(3, 256, 128), (130, 1024, 512), (64, 32000, 4096), (1024, 32000, 512)])
 def test_gemm_f16_logits(lib, impl, M, N, K):
     rng = np.random.default_rng(N)
     a = rng.standard_normal((M, K)).astype(np.float16)
     w = (0.02 * rng.standard_normal((N, K))).astype(np.float16)
     out = torch.zeros((M, N), dtype=torch.float32, device="cuda")
     rc = lib.b2llm_op_gemm_f16(stream_ptr(), _ptr(dev(a)), _ptr(dev(w)), M, N, K, capi.EPI_F32, _ptr(out), N, impl)
-    if impl == 2 and rc == 4:
+    if impl >= 2 and rc == 4:
         pytest.skip("tcgen05 path not built")
     capi.check(rc)
     sync()
