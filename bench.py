@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.t_begin = index, [], False, None
 
     def run(self):
         while not self.stop_flag:
@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 6:
-                    self.samples.append(f)
+                    self.samples.append(f + [time.perf_counter()])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -71,6 +71,11 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        # samples taken inside the timed region; a region shorter than one nvidia-smi call falls back to the samples
+        # taken under the identical warm-up load just before it
+        inside = [s for s in self.samples if self.t_begin is not None and s[-1] >= self.t_begin]
+        if inside:
+            self.samples = inside
         sm = sorted(int(s[0]) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
@@ -173,6 +178,9 @@ def main():
         reference_arm(args, args.kv_len or 496)
         return
 
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import b200_import
     b200_import.load()
@@ -242,12 +250,13 @@ def main():
 
     # stage inputs once for the device-resident measurement
     assert engine.SetInput(mi, True) == RC_SUCCESS
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
     lib.b2llm_engine_profile(res.engine, 1)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.t_begin = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -330,7 +339,8 @@ def main():
                 "sample": f"oracle (numpy/BLAS, all {cores} host threads) on batch {cb} of {BATCH} at kv_len {kv_len}: 1- and 2-layer "
                           f"runs timed, per-layer {per_layer * 1e3:.1f} ms x 32 + head {head * 1e3:.1f} ms = {st * 1e3:.0f} ms/step; "
                           f"builder-written port (the reference has no CPU backend, SURVEY.md F3)"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     res.close()
     if world > 1:
         dist.destroy_process_group()

@@ -45,7 +45,14 @@ enum {
 };
 
 /* quant_method: src/backends/cuda/resource_manager.cc:49-56 accepts "none" and "online_i8i8" */
-enum { B2LLM_QUANT_NONE = 0, B2LLM_QUANT_ONLINE_I8I8 = 1 };
+enum {
+    B2LLM_QUANT_NONE = 0,
+    B2LLM_QUANT_ONLINE_I8I8 = 1,
+    /* W4A16: NOT selectable in the reference at this commit (anything but the two above is rejected,
+     * resource_manager.cc:49-56), so its semantics are builder-defined: symmetric int4 weights, group 128
+     * along K, fp16 scales, fp16 activations, operand value fp16(q * scale).  Reachable through the C ABI only. */
+    B2LLM_QUANT_W4A16 = 2
+};
 
 /* Mirror of ppl::llm::ModelConfig (src/common/config.h:64-84, parsed by src/common/config.cc:31-148)
  * plus what the reference keeps in the exported graph rather than params.json (norm eps, rope
@@ -139,7 +146,7 @@ B2LLM_API int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t v
 
 /* weights.  load_weight takes the FULL (unsharded) fp16 tensor on the host and keeps this rank's
  * slice; with quant_method == online_i8i8 the projection weights are quantised per output channel on
- * load (the reference's "online" quantisation pass, resource_manager.cc:51-52).
+ * load (the reference's "online" quantisation pass, resource_manager.cc:51-52); with w4a16 to int4 group-128.
  * random_init fills every weight with the seeded synthetic generator. */
 B2LLM_API int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
                                            uint64_t num_elements);
@@ -245,7 +252,8 @@ B2LLM_API int32_t b2llm_op_rope_kv_append(void* stream, void* qkv_fp16, const b2
 /* attention for every token of the step: decode sequences read the int8 cache, prefill sequences
  * the fresh fp16 k/v in qkv (plus the cached prefix when step->cache_prefill).  out fp16
  * [num_tokens, nq * head_dim].  workspace: b2llm_attention_workspace_size bytes.
- * impl: 0 auto, 1 simple reference kernel, 2 tensor-core split-KV kernel */
+ * impl: 0 auto, 1 simple reference kernel for every token, 2 tensor-core kernels (split-KV flash-decoding for the
+ * decode sequences, flash-attention forward for the prefill sequences; head_dim 128) */
 B2LLM_API int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_heads, int32_t head_dim);
 B2LLM_API int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const b2llm_step* step, int32_t num_heads,
                                      const b2llm_kv_geom* geom, int32_t layer, const void* kv_cache,
@@ -259,6 +267,13 @@ B2LLM_API int32_t b2llm_op_synth_fp16(void* stream, uint64_t seed, uint64_t tens
 /* per-output-channel int8 quantisation of an fp16 weight [N, K] (device) */
 B2LLM_API int32_t b2llm_op_quant_weight(void* stream, const void* w_fp16, int32_t N, int32_t K, int8_t* q_out,
                                         float* scale_out);
+
+/* W4A16 weight preparation (B2LLM_QUANT_W4A16): int4 group-128 quantisation of an fp16 weight [N, K] (device) into packed
+ * nibbles [N, K/2] + fp16 scales [N, K/128], and its expansion to the fp16 GEMM operand fp16(q * scale) [N, K] */
+B2LLM_API int32_t b2llm_op_quant_weight_w4(void* stream, const void* w_fp16, int32_t N, int32_t K, uint8_t* packed_out,
+                                           void* scale_out_fp16);
+B2LLM_API int32_t b2llm_op_dequant_w4(void* stream, const uint8_t* packed, const void* scale_fp16, int32_t N, int32_t K,
+                                      void* w_out_fp16);
 
 #ifdef __cplusplus
 }

@@ -271,6 +271,12 @@ class LlamaOracle:
             wq, ws = self._slice_cache[key]
             q, s = quant_rows(xs.astype(F32))
             return dequant_acc(gemm_i8_acc(q, wq), s, ws).astype(np.float16)
+        if d.quant_method == 2:  # groups of 128 run along the rank's own K slice
+            key = (layer, name, r)
+            if key not in self._slice_cache:
+                from .weights import quantize_weight_w4
+                self._slice_cache[key] = quantize_weight_w4(np.ascontiguousarray(lw[name][:, lo:hi]))[2]
+            return gemm_f16_acc(xs, self._slice_cache[key]).astype(np.float16)
         return gemm_f16_acc(xs, lw[name][:, lo:hi]).astype(np.float16)
 
     def _row_parallel(self, x16: np.ndarray, lw, name: str, layer: int) -> np.ndarray:
@@ -291,6 +297,8 @@ class LlamaOracle:
             q, s = prequant if prequant is not None else quant_rows(x_f32_or_16)
             acc = gemm_i8_acc(q, lw[name + "_q"])
             return dequant_acc(acc, s, lw[name + "_s"])
+        if d.quant_method == 2:  # W4A16: fp16 activations x fp16(q * scale) weights, fp32 accumulate
+            return gemm_f16_acc(x_f32_or_16.astype(np.float16), lw[name + "_w4"])
         return gemm_f16_acc(x_f32_or_16.astype(np.float16), lw[name])
 
     def forward(self, step: Step, trace: dict | None = None, ulp_nudge: bool = False) -> np.ndarray:

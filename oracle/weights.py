@@ -74,6 +74,23 @@ def quantize_weight_per_channel(w16: np.ndarray):
     return q, scale
 
 
+def quantize_weight_w4(w16: np.ndarray, group: int = 128):
+    """W4A16 (builder-defined -- the reference rejects every quant method but "none" / "online_i8i8",
+    ``resource_manager.cc:49-56``): symmetric int4, one fp16 scale per ``group`` consecutive K elements of an output
+    channel.  scale16 = fp16(max|w| / 7); q = clamp(rint(w / fp32(scale16)), -7, 7) (0 where scale16 == 0).
+    Returns (q int8 [N, K], scale fp16 [N, K/group], dequantised operand fp16 [N, K] = fp16(q * scale))."""
+    N, K = w16.shape
+    w = w16.astype(np.float32).reshape(N, K // group, group)
+    amax = np.abs(w).max(axis=-1)
+    s16 = (amax / np.float32(7.0)).astype(np.float32).astype(np.float16)
+    s = s16.astype(np.float32)
+    safe = np.where(s > 0, s, np.float32(1.0))
+    q = np.where(s[..., None] > 0, np.rint(w / safe[..., None]), 0.0)
+    q = np.clip(q, -7, 7).astype(np.int8)
+    deq = (q.astype(np.float32) * s[..., None]).astype(np.float16).reshape(N, K)
+    return q.reshape(N, K), s16, deq
+
+
 class ModelDesc:
     """Mirror of ``ppl::llm::ModelConfig`` (``src/common/config.h:64-84``) plus the knobs that live
     in the exported graph rather than params.json (eps, rope theta; ``config.h:74``)."""
@@ -94,7 +111,7 @@ class ModelDesc:
         self.cache_layout = cache_layout
         self.cache_mode = cache_mode
         self.page_size = page_size
-        self.quant_method = quant_method  # 0 none (fp16), 1 online_i8i8
+        self.quant_method = quant_method  # 0 none (fp16), 1 online_i8i8, 2 w4a16 (builder-defined)
         self.max_position = max_position
 
     @property
@@ -162,6 +179,9 @@ class SynthWeights:
                     q, s = quantize_weight_per_channel(w[name])
                     w[name + "_q"] = q
                     w[name + "_s"] = s
+            elif d.quant_method == 2:
+                for name in ("wqkv", "wo", "wgate", "wup", "wdown"):
+                    w[name + "_w4"] = quantize_weight_w4(w[name])[2]  # the fp16 operand fp16(q * scale)
             return w
 
         return self._get(("layer", l), make)

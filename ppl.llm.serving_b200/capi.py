@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libb2llm.so"
 
 B2LLM_OK = 0
-QUANT_NONE, QUANT_ONLINE_I8I8 = 0, 1
+QUANT_NONE, QUANT_ONLINE_I8I8, QUANT_W4A16 = 0, 1, 2
 W_EMBEDDING, W_FINAL_NORM, W_LM_HEAD, W_ATTN_NORM, W_QKV, W_O, W_FFN_NORM, W_GATE, W_UP, W_DOWN = range(10)
 EPI_F16, EPI_RESIDUAL, EPI_SWIGLU, EPI_F32 = range(4)
 
@@ -83,6 +83,8 @@ SIGNATURES = {
     "b2llm_rope_table": (_I32, [_I32, _I32, _F, _P, _P]),
     "b2llm_op_synth_fp16": (_I32, [_P, _U64, _U64, _U64, _F, _F, _P]),
     "b2llm_op_quant_weight": (_I32, [_P, _P, _I32, _I32, _P, _P]),
+    "b2llm_op_quant_weight_w4": (_I32, [_P, _P, _I32, _I32, _P, _P]),
+    "b2llm_op_dequant_w4": (_I32, [_P, _P, _P, _I32, _I32, _P]),
 }
 
 _lib = None

@@ -699,11 +699,7 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
     auto kern = attn_decode_kernel<G, WARPS, TMA>;
     constexpr int smem_bytes = WARPS * NSTAGE * STAGE + 1024 + 8 * WARPS * NSTAGE + 64 +
                                (WARPS * G * 130 * 4 > WARPS * NSTAGE * STAGE ? WARPS * G * 130 * 4 : 0);
-    static bool configured = false;
-    if (!configured) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        configured = true;
-    }
+    B2_ENSURE_DYN_SMEM(kern, smem_bytes);
     const int gq = p.nq / p.nkv;
     const int chunks = (gq + G - 1) / G;
     dim3 grid(p.nsplit, p.nkv * chunks, p.decoding_batches);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/b2llm.h"
@@ -41,6 +42,22 @@ extern thread_local int64_t g_launch_count;  // kernels launched by this thread 
             return B2LLM_ERR_DEVICE;                                                      \
         }                                                                                 \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: in the reference's single-process
+// tensor parallelism (one host thread per GPU, resource_manager.cc:410-418) every device must set it once.
+// `mask` is a per-call-site bitmask of the devices already configured.
+#define B2_ENSURE_DYN_SMEM(kern, bytes)                                                                        \
+    do {                                                                                                       \
+        static std::atomic<uint64_t> b2_smem_mask_{0};                                                         \
+        int b2_dev_ = 0;                                                                                       \
+        B2_CHECK_CUDA(cudaGetDevice(&b2_dev_));                                                                \
+        const uint64_t b2_bit_ = 1ull << (b2_dev_ & 63);                                                       \
+        if (!(b2_smem_mask_.load(std::memory_order_acquire) & b2_bit_)) {                                      \
+            B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            b2_smem_mask_.fetch_or(b2_bit_, std::memory_order_release);                                        \
+        }                                                                                                      \
+    } while (0)
+
 
 // ------------------------------------------------------------------ KV addressing
 // Element strides of the int8 cache for the reference's four layouts (llm_engine.cc:118-169).
@@ -189,12 +206,15 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
                               int8_t* kv_cache, __half* kv_scale);
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end);
 int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a);
+int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a);  // sequences [decoding_batches, batch)
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim);
 
 int32_t launch_synth_fp16(cudaStream_t s, uint64_t seed, uint64_t tid, uint64_t n, float std, float mean, __half* out);
 int32_t launch_synth_fp16_2d(cudaStream_t s, uint64_t seed, uint64_t tid, int64_t rows, int64_t cols, int64_t row0,
                              int64_t col0, int64_t full_cols, float std, float mean, __half* out);
 int32_t launch_quant_weight(cudaStream_t s, const __half* w, int N, int K, int8_t* q, float* scale);
+int32_t launch_quant_weight_w4(cudaStream_t s, const __half* w, int N, int K, uint8_t* packed, __half* scale);
+int32_t launch_dequant_w4(cudaStream_t s, const uint8_t* packed, const __half* scale, int N, int K, __half* out);
 int32_t launch_interleave_rows(cudaStream_t s, const __half* a, const __half* b, int rows, int cols, __half* out);
 
 }  // namespace b2llm

@@ -91,7 +91,7 @@ struct b2llm_engine {
     DevBuf embedding, final_norm, lm_head;
     DevBuf rope_cos, rope_sin;
     // activations
-    DevBuf x, a8, a_s, qkv, attn, act, b8, b_s, tmp, y16, xl, yl, logits, attn_ws;
+    DevBuf x, a8, a_s, qkv, attn, act, b8, b_s, tmp, y16, xl, yl, logits, attn_ws, w16_scratch;
     // staged inputs
     DevBuf in_tokens, in_seq_starts, in_kv_starts, in_start_pos, in_cache_idx;
     b2llm_step staged{};
@@ -139,9 +139,15 @@ struct Span {  // RAII: records begin / end events around a kernel class when pr
 
 namespace {
 
-int32_t alloc_linear(Linear& L, int N, int K, bool i8) {
+int32_t alloc_linear(Linear& L, int N, int K, int quant_method) {
     L.N = N;
     L.K = K;
+    if (quant_method == B2LLM_QUANT_W4A16) {  // packed nibbles + one fp16 scale per 128 K-elements
+        int32_t rc = L.w.ensure((size_t)N * K / 2);
+        if (rc) return rc;
+        return L.scale.ensure((size_t)N * (K / 128) * sizeof(__half));
+    }
+    const bool i8 = quant_method == B2LLM_QUANT_ONLINE_I8I8;
     int32_t rc = L.w.ensure((size_t)N * K * (i8 ? 1 : 2));
     if (rc) return rc;
     if (i8) rc = L.scale.ensure((size_t)N * sizeof(float));
@@ -152,6 +158,8 @@ int32_t alloc_linear(Linear& L, int N, int K, bool i8) {
 int32_t finalize_linear(b2llm_engine* e, Linear& L, const __half* w16) {
     if (e->d.quant_method == B2LLM_QUANT_ONLINE_I8I8)
         return launch_quant_weight(e->stream, w16, L.N, L.K, L.w.as<int8_t>(), L.scale.as<float>());
+    if (e->d.quant_method == B2LLM_QUANT_W4A16)
+        return launch_quant_weight_w4(e->stream, w16, L.N, L.K, L.w.as<uint8_t>(), L.scale.as<__half>());
     B2_CHECK_CUDA(cudaMemcpyAsync(L.w.p, w16, (size_t)L.N * L.K * 2, cudaMemcpyDeviceToDevice, e->stream));
     return B2LLM_OK;
 }
@@ -160,6 +168,18 @@ int32_t gemm(b2llm_engine* e, const void* a, const float* a_scale, const Linear&
              int64_t ldc) {
     const bool i8 = e->d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
     Span span(e, 1);
+    if (e->d.quant_method == B2LLM_QUANT_W4A16) {
+        // v1: expand the int4 weight to its fp16 operand in a scratch buffer, then the fp16 tcgen05 GEMM.
+        // (Costs 4.5 B of HBM traffic per weight instead of 0.5; the in-kernel dequant is the next step)
+        __half* w16 = e->w16_scratch.as<__half>();
+        int32_t rc = launch_dequant_w4(e->stream, L.w.as<uint8_t>(), L.scale.as<__half>(), L.N, L.K, w16);
+        if (rc) return rc;
+        if (e->gemm_impl != 1 && gemm_tc_available()) {
+            rc = launch_gemm_tc(e->stream, false, a, nullptr, w16, nullptr, M, L.N, L.K, epi, out, ldc);
+            if (rc != B2LLM_ERR_UNSUPPORTED) return rc;
+        }
+        return launch_gemm_mma(e->stream, false, a, nullptr, w16, nullptr, M, L.N, L.K, epi, out, ldc);
+    }
     if (e->gemm_impl != 1 && gemm_tc_available()) {
         const int32_t rc = launch_gemm_tc(e->stream, i8, a, a_scale, L.w.p, L.scale.as<float>(), M, L.N, L.K, epi, out, ldc);
         if (rc != B2LLM_ERR_UNSUPPORTED) return rc;
@@ -212,8 +232,12 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     B2_REQUIRE(d.cache_layout >= 0 && d.cache_layout <= 3, B2LLM_ERR_INVALID_VALUE, "cache_layout must be 0..3");
     B2_REQUIRE(d.cache_mode == 0 || (d.cache_mode == 1 && d.page_size > 0), B2LLM_ERR_INVALID_VALUE,
                "cache_mode must be 0, or 1 with page_size > 0");
-    B2_REQUIRE(d.quant_method == B2LLM_QUANT_NONE || d.quant_method == B2LLM_QUANT_ONLINE_I8I8, B2LLM_ERR_UNSUPPORTED,
-               "quant_method must be none or online_i8i8");
+    B2_REQUIRE(d.quant_method == B2LLM_QUANT_NONE || d.quant_method == B2LLM_QUANT_ONLINE_I8I8 ||
+                   d.quant_method == B2LLM_QUANT_W4A16,
+               B2LLM_ERR_UNSUPPORTED, "quant_method must be none, online_i8i8 or w4a16");
+    B2_REQUIRE(d.quant_method != B2LLM_QUANT_W4A16 ||
+                   (d.hidden_dim % 128 == 0 && (d.intermediate_dim / tp) % 128 == 0 && (d.hidden_dim / tp) % 128 == 0),
+               B2LLM_ERR_UNSUPPORTED, "w4a16: every (per-rank) reduction dimension must be a multiple of the group size 128");
     B2_REQUIRE(d.max_tokens_per_step > 0 && d.max_running_batch > 0 && d.max_position > 0, B2LLM_ERR_INVALID_VALUE,
                "max_tokens_per_step / max_running_batch / max_position must be positive");
     int ndev = 0;
@@ -257,10 +281,14 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     for (auto& L : e->layers) {
         chk(L.attn_norm.ensure((size_t)h * 2));
         chk(L.ffn_norm.ensure((size_t)h * 2));
-        chk(alloc_linear(L.qkv, e->nqkv, h, i8));
-        chk(alloc_linear(L.o, h, e->nq * e->D, i8));
-        chk(alloc_linear(L.gate_up, 2 * e->inter, h, i8));
-        chk(alloc_linear(L.down, h, e->inter, i8));
+        chk(alloc_linear(L.qkv, e->nqkv, h, d.quant_method));
+        chk(alloc_linear(L.o, h, e->nq * e->D, d.quant_method));
+        chk(alloc_linear(L.gate_up, 2 * e->inter, h, d.quant_method));
+        chk(alloc_linear(L.down, h, e->inter, d.quant_method));
+    }
+    if (d.quant_method == B2LLM_QUANT_W4A16) {
+        const size_t big = std::max((size_t)std::max(e->nqkv, 2 * e->inter) * h, (size_t)h * std::max(e->inter, e->nq * e->D));
+        chk(e->w16_scratch.ensure(big * 2));
     }
     chk(e->embedding.ensure((size_t)d.vocab_size * h * 2));
     chk(e->final_norm.ensure((size_t)h * 2));
@@ -358,7 +386,7 @@ extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : {&e->embedding, &e->final_norm, &e->lm_head, &e->rope_cos, &e->rope_sin, &e->x, &e->a8, &e->a_s,
                       &e->qkv, &e->attn, &e->act, &e->b8, &e->b_s, &e->tmp, &e->y16, &e->xl, &e->yl, &e->logits,
-                      &e->attn_ws, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
+                      &e->attn_ws, &e->w16_scratch, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
                       &e->in_cache_idx})
         b->release();
     delete e;
@@ -675,7 +703,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
                 if ((rc = launch_attention_simple(s, aa, 0, T))) return rc;
             } else {
                 if ((rc = launch_attention_decode_mma(s, aa))) return rc;
-                if ((rc = launch_attention_simple(s, aa, decode_tokens, T))) return rc;
+                if (decode_tokens < T && (rc = launch_attention_prefill_mma(s, aa))) return rc;
             }
         }
         if (i8) {
@@ -867,7 +895,8 @@ extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const 
     B2_REQUIRE(workspace, B2LLM_ERR_INVALID_VALUE, "attention: workspace required");
     int32_t rc = launch_attention_decode_mma(s, aa);
     if (rc) return rc;
-    return launch_attention_simple(s, aa, step->decoding_batches, step->num_tokens);
+    if (step->decoding_batches >= step->batch) return B2LLM_OK;
+    return launch_attention_prefill_mma(s, aa);
 }
 
 extern "C" int32_t b2llm_op_synth_fp16(void* stream, uint64_t seed, uint64_t tensor_id, uint64_t num_elements, float std,
@@ -880,4 +909,16 @@ extern "C" int32_t b2llm_op_quant_weight(void* stream, const void* w_fp16, int32
                                          float* scale_out) {
     B2_REQUIRE(w_fp16 && q_out && scale_out, B2LLM_ERR_INVALID_VALUE, "quant_weight: null pointer");
     return launch_quant_weight((cudaStream_t)stream, (const __half*)w_fp16, N, K, q_out, scale_out);
+}
+
+extern "C" int32_t b2llm_op_quant_weight_w4(void* stream, const void* w_fp16, int32_t N, int32_t K, uint8_t* packed_out,
+                                            void* scale_out_fp16) {
+    B2_REQUIRE(w_fp16 && packed_out && scale_out_fp16, B2LLM_ERR_INVALID_VALUE, "quant_weight_w4: null pointer");
+    return launch_quant_weight_w4((cudaStream_t)stream, (const __half*)w_fp16, N, K, packed_out, (__half*)scale_out_fp16);
+}
+
+extern "C" int32_t b2llm_op_dequant_w4(void* stream, const uint8_t* packed, const void* scale_fp16, int32_t N, int32_t K,
+                                       void* w_out_fp16) {
+    B2_REQUIRE(packed && scale_fp16 && w_out_fp16, B2LLM_ERR_INVALID_VALUE, "dequant_w4: null pointer");
+    return launch_dequant_w4((cudaStream_t)stream, packed, (const __half*)scale_fp16, N, K, (__half*)w_out_fp16);
 }

@@ -132,11 +132,7 @@ int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* 
                int N, int Kb, void* out, int64_t ldc) {
     auto kern = gemm_mma_kernel<I8, EPI>;
     const int smem_bytes = STAGES * STAGE_BYTES;
-    static bool configured = false;  // per template instantiation
-    if (!configured) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        configured = true;
-    }
+    B2_ENSURE_DYN_SMEM(kern, smem_bytes);
     dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM));
     kern<<<grid, THREADS, smem_bytes, s>>>((const uint8_t*)a, a_scale, (const uint8_t*)w, w_scale, (int)M, N, Kb, out,
                                            ldc);

@@ -503,21 +503,30 @@ bool cached_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t Kb, u
     return true;
 }
 
+// number of SMs the persistent GEMM grids may occupy (B2LLM_GEMM_SMS; default all).  A smaller budget leaves SMs to a
+// kernel running concurrently on another stream (scripts/overlap_probe.py).
+int gemm_sm_budget() {
+    static int budget = [] {
+        const char* e = getenv("B2LLM_GEMM_SMS");
+        const int n = e ? atoi(e) : 0;
+        const int sms = device_num_sms();
+        return (n >= 2 && n <= sms) ? n : sms;
+    }();
+    return budget;
+}
+
 template <bool I8, int EPI, int BN>
 int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* w, const float* w_scale, int64_t M, int N,
                int Kb, void* out, int64_t ldc) {
     using C = Cfg<BN>;
     auto kern = gemm_tc_kernel<I8, EPI, BN>;
-    static bool configured = false;
-    if (!configured) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    B2_ENSURE_DYN_SMEM(kern, C::SMEM_BYTES);
     CUtensorMap ma, mw;
     B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)Kb, BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
     B2_REQUIRE(cached_map(&mw, w, (uint64_t)N, (uint64_t)Kb, BN), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W) failed");
     const int tiles = (int)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
+    const int sms = gemm_sm_budget();
+    const int grid = tiles < sms ? tiles : sms;
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
@@ -528,16 +537,12 @@ int32_t launch_pair(cudaStream_t s, const void* a, const float* a_scale, const v
                     int Kb, void* out, int64_t ldc) {
     using C = Cfg2;
     auto kern = gemm_tc2_kernel<I8, EPI>;
-    static bool configured = false;
-    if (!configured) {
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    B2_ENSURE_DYN_SMEM(kern, C::SMEM_BYTES);
     CUtensorMap ma, mw;
     B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)Kb, BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
     B2_REQUIRE(cached_map(&mw, w, (uint64_t)N, (uint64_t)Kb, BN2 / 2), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W) failed");
     const int tiles = (int)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
-    const int max_pairs = device_num_sms() / 2;
+    const int max_pairs = gemm_sm_budget() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
     kern<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
     B2_LAUNCH_CHECK();

@@ -46,6 +46,65 @@ __global__ void __launch_bounds__(256) quant_weight_kernel(const __half* __restr
     }
 }
 
+// W4A16 (builder-defined: the reference cannot select it, resource_manager.cc:49-56): symmetric int4, one fp16 scale
+// per 128 consecutive K elements of an output channel; scale16 = fp16(max|w| / 7), q = clamp(rint(w / scale16), -7, 7),
+// stored as the nibble q + 8, element k in the low (k even) / high (k odd) half of byte k / 2.
+// One warp per (row, group): lane l owns elements [4 l, 4 l + 4) of the group.
+__global__ void __launch_bounds__(256) quant_weight_w4_kernel(const __half* __restrict__ w, int64_t groups_total, int K,
+                                                             uint8_t* __restrict__ packed, __half* __restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gi >= groups_total) return;
+    const int gpr = K / 128;
+    const int64_t n = gi / gpr;
+    const int g = (int)(gi - n * gpr);
+    const __half* src = w + n * K + g * 128 + 4 * lane;
+    float v[4];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = __half2float(src[i]);
+        amax = fmaxf(amax, fabsf(v[i]));
+    }
+    amax = warp_max(amax);
+    const __half s16 = __float2half_rn(__fdiv_rn(amax, 7.0f));
+    const float sf = __half2float(s16);
+    uint32_t nib[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = sf > 0.f ? max(-7, min(7, __float2int_rn(__fdiv_rn(v[i], sf)))) : 0;
+        nib[i] = (uint32_t)(q + 8);
+    }
+    uint8_t* dst = packed + (n * K + g * 128 + 4 * lane) / 2;
+    dst[0] = (uint8_t)(nib[0] | (nib[1] << 4));
+    dst[1] = (uint8_t)(nib[2] | (nib[3] << 4));
+    if (lane == 0) scale[gi] = s16;
+}
+
+// fp16 [N, K] <- fp16(q * scale): the operand the fp16 tensor-core GEMM consumes.  16 bytes (32 weights) per thread.
+__global__ void __launch_bounds__(256) dequant_w4_kernel(const uint8_t* __restrict__ packed, const __half* __restrict__ scale,
+                                                        int64_t chunks, __half* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // chunk of 32 weights
+    if (c >= chunks) return;
+    const uint4 raw = *reinterpret_cast<const uint4*>(packed + c * 16);
+    const float sf = __half2float(scale[c / 4]);  // 4 chunks per 128-element group
+    const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint4 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q0 = (int)((wds[i] >> (8 * j)) & 0xF) - 8, q1 = (int)((wds[i] >> (8 * j + 4)) & 0xF) - 8;
+            const __half2 h = __floats2half2_rn(__fmul_rn((float)q0, sf), __fmul_rn((float)q1, sf));
+            ow[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = o[i];
+}
+
 // out[2 r] = a[r], out[2 r + 1] = b[r]
 __global__ void interleave_rows_kernel(const __half* __restrict__ a, const __half* __restrict__ b, int cols,
                                        __half* __restrict__ out) {
@@ -80,6 +139,24 @@ int32_t launch_synth_fp16(cudaStream_t s, uint64_t seed, uint64_t tid, uint64_t 
 int32_t launch_quant_weight(cudaStream_t s, const __half* w, int N, int K, int8_t* q, float* scale) {
     if (N == 0) return B2LLM_OK;
     quant_weight_kernel<<<N, 256, 0, s>>>(w, K, q, scale);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_quant_weight_w4(cudaStream_t s, const __half* w, int N, int K, uint8_t* packed, __half* scale) {
+    B2_REQUIRE(K % 128 == 0, B2LLM_ERR_UNSUPPORTED, "W4A16: K must be a multiple of the quantisation group (128)");
+    if (N == 0) return B2LLM_OK;
+    const int64_t groups = (int64_t)N * (K / 128);
+    quant_weight_w4_kernel<<<(unsigned)((groups + 7) / 8), 256, 0, s>>>(w, groups, K, packed, scale);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_dequant_w4(cudaStream_t s, const uint8_t* packed, const __half* scale, int N, int K, __half* out) {
+    B2_REQUIRE(K % 128 == 0, B2LLM_ERR_UNSUPPORTED, "W4A16: K must be a multiple of the quantisation group (128)");
+    if (N == 0) return B2LLM_OK;
+    const int64_t chunks = (int64_t)N * K / 32;
+    dequant_w4_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(packed, scale, chunks, out);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

@@ -40,7 +40,9 @@ def create_comm(world_size: int, rank: int) -> C.c_void_p:
         rc = lib.ncclGetUniqueId(C.byref(uid))
         if rc != 0:
             raise RuntimeError(f"ncclGetUniqueId: {lib.ncclGetErrorString(rc).decode()}")
-    buf = torch.tensor(list(bytes(uid.internal)) if rank == 0 else [0] * _NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+    # NB: reading a c_char array field stops at the first NUL -- copy the raw 128 bytes instead
+    raw = C.string_at(C.byref(uid), _NCCL_UNIQUE_ID_BYTES)
+    buf = torch.tensor(list(raw) if rank == 0 else [0] * _NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
     if dist.get_backend() == "nccl":
         buf = buf.cuda()
     dist.broadcast(buf, src=0)

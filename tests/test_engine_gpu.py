@@ -155,6 +155,29 @@ def test_w8a8_7b_dims_two_layers_batch():
     assert np.median(rels) <= 1e-4
 
 
+def test_generation_w4a16():
+    """builder-defined W4A16 (int4 group-128 weights, fp16 activations): the reference cannot select it"""
+    desc = ModelDesc(512, 1024, 2, 4, 2, 1024, cache_layout=3, cache_mode=1, page_size=16, quant_method=2, max_position=256)
+    _run_generation(desc, [16, 5], 5, seed=8, kv_tokens=512)
+
+
+def test_config4_70b_gqa_w4a16_rank_slice_dims():
+    """BASELINE.json configs[3] at the shape ONE rank of TP=8 sees, 2 layers: LLaMA-2-70B has hidden 8192, 64 q / 8 kv
+    heads, intermediate 28672; a rank holds 8 q heads over 1 kv head and 3584 intermediate channels.  Run as a
+    stand-alone model with those local dims (hidden 1024 keeps head_dim 128 and the 8:1 GQA group) so the per-rank
+    kernels -- GQA decode attention with G = 8, W4A16 GEMMs at the rank's K -- are exercised on one GPU."""
+    desc = ModelDesc(1024, 3584, 2, 8, 1, 32000, cache_layout=3, cache_mode=1, page_size=16, quant_method=2, max_position=512)
+    mism, rels = _run_generation(desc, [40, 3, 129], 4, seed=9, kv_tokens=1024)
+    assert mism == 0
+
+
+def test_config3_13b_dims_two_layers():
+    """BASELINE.json configs[2] dims (LLaMA-2-13B: hidden 5120, 40 heads, intermediate 13824), W8A8, 2 layers, TP=1"""
+    desc = ModelDesc(5120, 13824, 2, 40, 40, 32000, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=256)
+    mism, rels = _run_generation(desc, [9, 30], 3, seed=12, kv_tokens=512)
+    assert mism == 0
+
+
 def test_engine_errors_are_retcodes():
     desc = ModelDesc(256, 512, 1, 2, 2, 512, max_position=64)
     res = CudaResourceManager()

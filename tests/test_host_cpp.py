@@ -35,7 +35,7 @@ needs_ref = pytest.mark.skipif(not DRIVER.exists(), reason="oracle/_ref not buil
 
 def _run(cmd, **kw):
     env = dict(os.environ, PPL_LOG_LEVEL=kw.pop("log", "WARNING"))
-    return subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=kw.pop("timeout", 600), env=env)
+    return subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=kw.pop("timeout", 240), env=env)
 
 
 def test_host_library_exports_plugin_surface():

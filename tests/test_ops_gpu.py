@@ -65,6 +65,28 @@ def test_quant_weight_bit_exact(lib):
 
 
 # ------------------------------------------------------------------ norm / quant
+def test_w4a16_weight_quant_bit_exact(lib):
+    """int4 group-128 weight quantisation and its fp16 operand expansion (builder-defined W4A16)"""
+    from oracle.weights import quantize_weight_w4
+    rng = np.random.default_rng(4)
+    N, K = 96, 512
+    w = (0.02 * rng.standard_normal((N, K))).astype(np.float16)
+    w[5, 128:256] = 0          # an all-zero group: scale 0, codes 0 (nibble 8)
+    w[7, 3] = np.float16(0.5)  # an outlier dominating its group
+    q, s16, deq = quantize_weight_w4(w)
+    packed = torch.zeros((N, K // 2), dtype=torch.uint8, device="cuda")
+    scale = torch.zeros((N, K // 128), dtype=torch.float16, device="cuda")
+    capi.check(lib.b2llm_op_quant_weight_w4(stream_ptr(), _ptr(dev(w)), N, K, _ptr(packed), _ptr(scale)))
+    sync()
+    pk = packed.cpu().numpy()
+    assert np.array_equal((pk & 0xF).astype(np.int8) - 8, q[:, 0::2]) and np.array_equal((pk >> 4).astype(np.int8) - 8, q[:, 1::2])
+    assert np.array_equal(scale.cpu().numpy().view(np.uint16), s16.view(np.uint16))
+    out = torch.zeros((N, K), dtype=torch.float16, device="cuda")
+    capi.check(lib.b2llm_op_dequant_w4(stream_ptr(), _ptr(packed), _ptr(scale), N, K, _ptr(out)))
+    sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), deq.view(np.uint16))
+
+
 @pytest.mark.parametrize("rows,hidden", [(1, 256), (37, 4096), (5, 5120), (3, 11008)])
 def test_rmsnorm_quant(lib, rows, hidden):
     rng = np.random.default_rng(rows * 7 + hidden)
@@ -333,6 +355,17 @@ def test_attention_mixed_prefill_decode(lib, impl):
     desc = _mk_desc(3, 1, nq=4, nkv=2)
     # 2 decoding sequences first, then a fresh prompt and a prompt with a cached prefix
     _attention_case(lib, desc, [1, 1, 9, 6], [64, 7, 0, 32], 2, impl, seed=11)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("nq,nkv", [(4, 4), (8, 2)])
+def test_attention_prefill_tiles_and_prefixes(lib, impl, nq, nkv):
+    """prefill sequences spanning several 64-query tiles / 64-key blocks, tile-boundary lengths, cached prefixes that
+    are not multiples of the block, mixed with decode sequences (tensor-core flash-attention kernel for impl 2)"""
+    desc = _mk_desc(3, 1, nq=nq, nkv=nkv)
+    _attention_case(lib, desc, [1, 200, 64, 65, 1, 130], [77, 0, 0, 48, 0, 100], 1, impl, T_cache=4096, seed=21)
+    desc = _mk_desc(1, 0, nq=nq, nkv=nkv)
+    _attention_case(lib, desc, [300, 17], [0, 250], 0, impl, T_cache=4096, seed=22)
 
 
 def test_attention_long_ragged_batch(lib):
