@@ -330,7 +330,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU leg runs on rank 0 at N = 1 only
             cores = os.cpu_count()
             cb = 32
             tps, st, per_layer, head = cpu_tokens_per_s(cb, kv_len)

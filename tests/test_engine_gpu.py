@@ -189,3 +189,63 @@ def test_engine_errors_are_retcodes():
     rc, err = engine.Execute(mi, True, False, out)  # 64 tokens > max_tokens_per_step 32
     assert rc != RC_SUCCESS and "max_tokens_per_step" in err
     res.close()
+
+
+def test_full_size_paging_invariance_and_split_modes():
+    """BASELINE.json configs[1] at its full running batch (1024 sequences x 512 cached tokens, LLaMA-2-7B dims, W8A8,
+    int8 paged KV), one layer -- too big for the oracle, so size-independent properties are checked instead:
+      * the physical placement of pages is invisible: two caches holding the same logical K/V under two different
+        page permutations give bit-identical logits and tokens;
+      * the split-KV modes of decode attention (ENGINE_CONF_DECODING_ATTN_SPLIT_K 0 / 1 / 2) agree to fp32 rounding;
+      * every row is finite and rows with identical inputs are identical (batch independence)."""
+    import ctypes as C
+    from ppl_llm_serving_b200 import capi
+    from ppl_llm_serving_b200.engine import _ptr
+    B, KV, PAGE = 1024, 512, 16
+    desc = ModelDesc(4096, 11008, 1, 32, 32, 32000, cache_layout=3, cache_mode=1, page_size=PAGE, quant_method=1, max_position=1024)
+    T = B * KV
+    res = CudaResourceManager()
+    assert res.Init(desc, 0.9, B, B, kv_cache_max_tokens=T, seed=0xB200) == RC_SUCCESS
+    engine = LLMEngine(res, False, 1, 0.0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    H, D = 32, 128
+    logical = torch.randint(-127, 128, (2 * H, T, D), dtype=torch.int8, device="cuda", generator=g)
+    logical_s = (torch.rand((2 * H, T, D // 8), device="cuda", generator=g) * 0.02 + 0.001).to(torch.float16)
+    rng = np.random.default_rng(2)
+    tokens = rng.integers(0, desc.vocab_size, B).astype(np.int64)
+    tokens[1] = tokens[0]
+    # sequences 0 and 1 get identical history and token: their logits rows must be identical
+    logical[:, KV:2 * KV] = logical[:, 0:KV]
+    logical_s[:, KV:2 * KV] = logical_s[:, 0:KV]
+    outs = []
+    for seed in (10, 11):
+        perm = np.random.default_rng(seed).permutation(T // PAGE)
+        page_list = (perm.reshape(B, KV // PAGE) * PAGE).astype(np.int64)
+        slot = torch.from_numpy((page_list[:, :, None] + np.arange(PAGE)[None, None, :]).reshape(-1)).cuda()  # logical j -> slot
+        cache = res.kv_cache_mem.view(2 * H, T, D)
+        scale = res.kv_scale_mem.view(2 * H, T, D // 8)
+        cache.index_copy_(1, slot, logical)
+        scale.index_copy_(1, slot, logical_s)
+        mi = ModelInput(token_inputs=tokens, seq_starts=np.arange(B + 1, dtype=np.int64), kv_starts=np.arange(B + 1, dtype=np.int64) * KV,
+                        start_pos=np.full(B, KV - 1, dtype=np.int64), page_list=page_list.reshape(-1), max_pages=KV // PAGE,
+                        decoding_batches=B, max_seq_len=1, max_kv_len=KV, temperatures=[1.0] * B, top_p_list=[0.0] * B,
+                        top_k_list=[1] * B)
+        per_mode = []
+        for mode in (1, 0, 2):
+            capi.check(res.lib.b2llm_engine_configure(res.engine, 3, mode), "configure split-k")
+            out = ModelOutput()
+            out.Resize(B)
+            rc, err = engine.Execute(mi, True, False, out)
+            assert rc == RC_SUCCESS, err
+            per_mode.append((engine.logits(B), out.output_token.copy()))
+        capi.check(res.lib.b2llm_engine_configure(res.engine, 3, 1), "configure split-k")
+        outs.append(per_mode)
+    (la, ta), (lb, tb) = outs[0][0], outs[1][0]
+    assert np.isfinite(la).all()
+    assert np.array_equal(la, lb) and np.array_equal(ta, tb), "logits depend on the physical page placement"
+    assert np.array_equal(la[0], la[1]) and ta[0] == ta[1], "identical sequences gave different rows"
+    for l_mode, t_mode in outs[0][1:]:
+        rel = np.abs(l_mode - la).max(axis=1) / np.abs(la).max(axis=1)
+        # different split counts change only the fp32 merge order; a one-ulp flip of a W8A8 row max is possible but rare
+        assert np.median(rel) <= 1e-5 and (rel <= 1e-3).mean() >= 0.99, (np.median(rel), rel.max())
+    res.close()
