@@ -140,7 +140,8 @@ B2LLM_API int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int6
 enum {
     B2LLM_CONF_DECODING_ATTN_SPLIT_K = 3, /* 0 never split the KV range, 1 heuristic (default), 2 always */
     B2LLM_CONF_ATTN_IMPL = 100,           /* 0 auto, 1 simple reference kernel, 2 tensor-core split-KV kernel */
-    B2LLM_CONF_GEMM_IMPL = 101            /* 0 auto, 1 mma.sync baseline, 2 tcgen05 */
+    B2LLM_CONF_GEMM_IMPL = 101            /* 0 auto, 1 mma.sync baseline, 2 tcgen05; W4A16: 0/2 fused kernel, 1/3 dequant +
+                                             fp16 GEMM cross-check path */
 };
 B2LLM_API int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t value);
 
@@ -274,6 +275,11 @@ B2LLM_API int32_t b2llm_op_quant_weight_w4(void* stream, const void* w_fp16, int
                                            void* scale_out_fp16);
 B2LLM_API int32_t b2llm_op_dequant_w4(void* stream, const uint8_t* packed, const void* scale_fp16, int32_t N, int32_t K,
                                       void* w_out_fp16);
+
+/* fused W4A16 GEMM: C[m, n] = sum_k A[m, k] (fp16) * fp16(q[n, k] * scale[n, k / 128]), fp32 accumulation on tcgen05;
+ * epilogue 0 / 1 / 2 as b2llm_op_gemm_w8a8.  B2LLM_ERR_UNSUPPORTED when K % 128 != 0 or N % 128 != 0. */
+B2LLM_API int32_t b2llm_op_gemm_w4a16(void* stream, const void* a_fp16, const uint8_t* packed, const void* scale_fp16,
+                                      int64_t M, int32_t N, int32_t K, int32_t epilogue, void* out_fp16);
 
 #ifdef __cplusplus
 }

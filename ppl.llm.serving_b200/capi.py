@@ -85,6 +85,7 @@ SIGNATURES = {
     "b2llm_op_quant_weight": (_I32, [_P, _P, _I32, _I32, _P, _P]),
     "b2llm_op_quant_weight_w4": (_I32, [_P, _P, _I32, _I32, _P, _P]),
     "b2llm_op_dequant_w4": (_I32, [_P, _P, _P, _I32, _I32, _P]),
+    "b2llm_op_gemm_w4a16": (_I32, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
 }
 
 _lib = None

@@ -188,6 +188,8 @@ int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a
                        const float* w_scale, int64_t M, int N, int K, int epilogue, void* out, int64_t ldc,
                        int pair_mode = -1);  // -1 default (B2LLM_GEMM_2CTA), 0 single-CTA kernel, 2 CTA-pair kernel
 bool gemm_tc_available();
+int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* packed, const void* scale_fp16, int64_t M, int N,
+                          int K, int epilogue, void* out, int64_t ldc);
 
 struct AttnArgs {
     const __half* qkv;     // [T, (nq + 2 nkv) * D]

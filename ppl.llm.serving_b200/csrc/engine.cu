@@ -169,8 +169,13 @@ int32_t gemm(b2llm_engine* e, const void* a, const float* a_scale, const Linear&
     const bool i8 = e->d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
     Span span(e, 1);
     if (e->d.quant_method == B2LLM_QUANT_W4A16) {
-        // v1: expand the int4 weight to its fp16 operand in a scratch buffer, then the fp16 tcgen05 GEMM.
-        // (Costs 4.5 B of HBM traffic per weight instead of 0.5; the in-kernel dequant is the next step)
+        // fused kernel: packed nibbles -> smem -> converter warps -> tcgen05 (0.5 B of HBM traffic per weight)
+        if (e->gemm_impl == 0 || e->gemm_impl == 2) {
+            const int32_t rcf = launch_gemm_w4a16(e->stream, a, L.w.as<uint8_t>(), L.scale.p, M, L.N, L.K, epi, out, ldc);
+            if (rcf != B2LLM_ERR_UNSUPPORTED) return rcf;
+        }
+        // fallback / cross-check (B2LLM_GEMM_IMPL=1 or 3): expand the int4 weight to its fp16 operand in a scratch buffer,
+        // then the fp16 GEMM (4.5 B of traffic per weight)
         __half* w16 = e->w16_scratch.as<__half>();
         int32_t rc = launch_dequant_w4(e->stream, L.w.as<uint8_t>(), L.scale.as<__half>(), L.N, L.K, w16);
         if (rc) return rc;
@@ -366,7 +371,7 @@ extern "C" int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t 
             e->attn_impl = (int)value;
             return B2LLM_OK;
         case B2LLM_CONF_GEMM_IMPL:
-            B2_REQUIRE(value >= 0 && value <= 2, B2LLM_ERR_INVALID_VALUE, "configure: gemm impl must be 0, 1 or 2");
+            B2_REQUIRE(value >= 0 && value <= 3, B2LLM_ERR_INVALID_VALUE, "configure: gemm impl must be 0..3");
             e->gemm_impl = (int)value;
             return B2LLM_OK;
         default:
@@ -921,4 +926,12 @@ extern "C" int32_t b2llm_op_dequant_w4(void* stream, const uint8_t* packed, cons
                                        void* w_out_fp16) {
     B2_REQUIRE(packed && scale_fp16 && w_out_fp16, B2LLM_ERR_INVALID_VALUE, "dequant_w4: null pointer");
     return launch_dequant_w4((cudaStream_t)stream, packed, (const __half*)scale_fp16, N, K, (__half*)w_out_fp16);
+}
+
+extern "C" int32_t b2llm_op_gemm_w4a16(void* stream, const void* a_fp16, const uint8_t* packed, const void* scale_fp16, int64_t M,
+                                       int32_t N, int32_t K, int32_t epilogue, void* out_fp16) {
+    B2_REQUIRE(a_fp16 && packed && scale_fp16 && out_fp16, B2LLM_ERR_INVALID_VALUE, "gemm_w4a16: null pointer");
+    B2_REQUIRE(epilogue >= 0 && epilogue <= 2, B2LLM_ERR_INVALID_VALUE, "gemm_w4a16: epilogue must be 0, 1 or 2");
+    const int64_t ldc = epilogue == EPI_SWIGLU ? N / 2 : N;
+    return launch_gemm_w4a16((cudaStream_t)stream, a_fp16, packed, scale_fp16, M, N, K, epilogue, out_fp16, ldc);
 }

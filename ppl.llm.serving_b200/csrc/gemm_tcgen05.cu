@@ -477,6 +477,204 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     }
 }
 
+// ---------------------------------------------------------------- W4A16: int4 group-128 weights, dequant fused into operand staging
+// C[M,N] = A[M,K] (fp16) x fp16(q[N,K] * scale[N, K/128])^T, fp32 accumulation in TMEM (tcgen05.mma kind::f16).
+// The packed nibbles travel HBM -> smem as they are (0.5 B per weight, TMA, BN x 32 B per 64-element k-block); four
+// converter warps expand them to the fp16 operand value fp16(q * scale) -- the oracle's definition, bit for bit --
+// straight into the 128-byte-swizzled K-major tile the UMMA descriptor expects, make the writes visible to the async
+// proxy and arrive on the stage's b_full barrier.  One weight tile feeds up to two 128-row A tiles (M <= 256 per
+// CTA, the decode batch of BASELINE config 4 per rank), so the conversion cost is paid once per 256 rows.
+//   warp 0     TMA producer (A tiles + packed W)          warps 2-5   converters (thread = one output channel)
+//   warp 1     TMEM alloc + MMA issuer                    warps 6-9   epilogue (TMEM lane quarter = warp % 4)
+constexpr int W4_BN = 128;
+constexpr int W4_THREADS = 320;
+template <int MT>
+struct CfgW4 {
+    static constexpr int STAGES = MT == 2 ? 4 : 5;
+    static constexpr int A_BYTES = MT * BM * BKB;          // 16 / 32 KB
+    static constexpr int RAW_BYTES = W4_BN * (BKB / 4);    // 4 KB: 64 nibbles = 32 B per row
+    static constexpr int B_BYTES = W4_BN * BKB;            // 16 KB
+    static constexpr int STAGE_BYTES = A_BYTES + RAW_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = MT == 2 ? 512 : 256;  // 2 buffers x MT x 128 columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 8 nibbles (one uint32, element i in bits [4i, 4i+4)) -> 8 fp16 values (q - 8) * scale as 4 packed half2
+__device__ __forceinline__ uint4 w4_expand8(uint32_t w, __half2 sc) {
+    const __half2 bias = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));  // 1032 = 1024 + 8
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t b = (w >> (8 * i)) & 0xFFu;                                   // elements 2i (low nibble), 2i + 1
+        uint32_t pk = (b & 0xFu) | ((b >> 4) << 16) | 0x64006400u;                  // halves 1024 + nibble
+        __half2 h = *reinterpret_cast<__half2*>(&pk);
+        h = __hmul2(__hsub2(h, bias), sc);                                           // exact q, one rounding: fp16(q * s)
+        o[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int EPI, int MT>
+__global__ void __launch_bounds__(W4_THREADS, 1)
+    gemm_w4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc) {
+    using C = CfgW4<MT>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto afull_bar = [&](int s) { return bars + 8u * s; };
+    auto bfull_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (3 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (3 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * C::STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (M + MT * BM - 1) / (MT * BM), num_n = N / W4_BN;
+    const int num_tiles = num_m * num_n;
+    const int nk = (2 * K) / BKB;   // k-blocks of 64 elements (128 bytes of fp16)
+    const int gpr = K / 128;        // scale groups per output channel
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(afull_bar(s), 1);
+            mbar_init(bfull_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_w);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sraw = sa + C::A_BYTES;
+                    mbar_expect_tx(afull_bar(stage), C::A_BYTES + C::RAW_BYTES);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        tma_load_2d(sa + mt * BM * BKB, &map_a, afull_bar(stage), kb * BKB, (m_blk * MT + mt) * BM);
+                    tma_load_2d(sraw, &map_w, afull_bar(stage), kb * (BKB / 4), n_blk * W4_BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<false>(W4_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * (MT * W4_BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(afull_bar(stage), phase);
+                    mbar_wait(bfull_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES + C::RAW_BYTES;
+                    const uint64_t db = make_smem_desc(sb);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t da = make_smem_desc(sa + mt * BM * BKB);
+#pragma unroll
+                        for (int k = 0; k < BKB / 32; ++k)
+                            tc_mma<false>(tmem_c + mt * W4_BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));
+            }
+        }
+    } else if (warp < 6) {
+        // converters: thread r owns output channel (row) r of the weight tile
+        const int r = threadIdx.x - 64;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile / num_m;
+            const __half* srow = w_scale + (int64_t)(n_blk * W4_BN + r) * gpr;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(afull_bar(stage), phase);
+                const uint32_t sraw = smem_base + stage * C::STAGE_BYTES + C::A_BYTES, sb = sraw + C::RAW_BYTES;
+                const __half sc1 = srow[kb >> 1];  // 64-element k-blocks, 128-element groups
+                const __half2 sc = __halves2half2(sc1, sc1);
+                uint4 raw[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(raw[j].x), "=r"(raw[j].y), "=r"(raw[j].z), "=r"(raw[j].w)
+                                 : "r"(sraw + r * 32 + j * 16));
+                const uint32_t wds[8] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w, raw[1].x, raw[1].y, raw[1].z, raw[1].w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {  // 16-byte chunk c = elements [8c, 8c + 8) of the k-block
+                    const uint4 v = w4_expand8(wds[c], sc);
+                    const uint32_t dst = sb + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(bfull_bar(stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int m = (m_blk * MT + mt) * BM + quarter * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MT * W4_BN) + mt * W4_BN;
+#pragma unroll 1
+                for (int c = 0; c < W4_BN / 32; ++c) {
+                    const int n0 = n_blk * W4_BN + c * 32;
+                    uint32_t rr[32];
+                    tmem_ld32(taddr + c * 32, rr);
+                    if (m < M) epilogue_store32<false, EPI>(rr, m, n0, 1.f, nullptr, out, ldc);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
+}
+
 // ---------------------------------------------------------------- host side
 // 2D byte tensor [rows, Kb] with a (128 B x box_rows) box and 128 B swizzle; out-of-range rows read as zero
 bool encode_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t Kb, uint32_t box_rows) {
@@ -577,9 +775,58 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
     return launch<I8, EPI, 128>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
 }
 
+template <int EPI, int MT>
+int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __half* scale, int64_t M, int N, int K, void* out,
+                  int64_t ldc) {
+    using C = CfgW4<MT>;
+    auto kern = gemm_w4_kernel<EPI, MT>;
+    B2_ENSURE_DYN_SMEM(kern, C::SMEM_BYTES);
+    CUtensorMap ma, mw;
+    B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)(2 * K), BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
+    {  // packed weights: [N, K/2] bytes, box {32 B, 128 rows}, no swizzle
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto key = std::make_tuple((const void*)packed, (uint64_t)N, (uint64_t)(K / 2), (uint32_t)0xFFFF0004u);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) {
+            mw = it->second;
+        } else {
+            const uint64_t dims[2] = {(uint64_t)(K / 2), (uint64_t)N};
+            const uint64_t strides[1] = {(uint64_t)(K / 2)};
+            const uint32_t box[2] = {(uint32_t)(BKB / 4), (uint32_t)W4_BN};
+            B2_REQUIRE(tma_encode_bytes(&mw, packed, 2, dims, strides, box, false), B2LLM_ERR_DEVICE,
+                       "cuTensorMapEncodeTiled(W4) failed");
+            g_map_cache[key] = mw;
+        }
+    }
+    const int tiles = (int)((M + MT * BM - 1) / (MT * BM)) * (N / W4_BN);
+    const int sms = gemm_sm_budget();
+    const int grid = tiles < sms ? tiles : sms;
+    kern<<<grid, W4_THREADS, C::SMEM_BYTES, s>>>(ma, mw, scale, (int)M, N, K, out, ldc);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
 }  // namespace
 
 bool gemm_tc_available() { return tma_available(); }
+
+// fused W4A16 GEMM; B2LLM_ERR_UNSUPPORTED for shapes outside its envelope (caller falls back to dequant + fp16 GEMM)
+int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* packed, const void* scale_fp16, int64_t M, int N, int K,
+                          int epilogue, void* out, int64_t ldc) {
+    if (!gemm_tc_available() || K % 128 != 0 || N % W4_BN != 0 || M >= (1ll << 31) || ((uintptr_t)a_fp16 & 15) ||
+        ((uintptr_t)packed & 15) || ((uintptr_t)out & 15) || (ldc % 8) != 0 || epilogue < EPI_F16 || epilogue > EPI_SWIGLU) {
+        set_last_error("tcgen05 w4a16 gemm: shape / alignment outside the kernel envelope");
+        return B2LLM_ERR_UNSUPPORTED;
+    }
+    if (M == 0) return B2LLM_OK;
+    const __half* sc = (const __half*)scale_fp16;
+    const bool two = M > BM;
+    switch (epilogue) {
+        case EPI_F16: return two ? launch_w4<EPI_F16, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_F16, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+        case EPI_RESIDUAL: return two ? launch_w4<EPI_RESIDUAL, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_RESIDUAL, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+        default: return two ? launch_w4<EPI_SWIGLU, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_SWIGLU, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+    }
+}
 
 int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w, const float* w_scale,
                        int64_t M, int N, int K, int epilogue, void* out, int64_t ldc, int pair_mode) {

@@ -87,6 +87,37 @@ def test_w4a16_weight_quant_bit_exact(lib):
     assert np.array_equal(out.cpu().numpy().view(np.uint16), deq.view(np.uint16))
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 128, 128), (100, 256, 512), (256, 1280, 8192), (129, 384, 1024), (300, 512, 256)])
+def test_gemm_w4a16_fused(lib, M, N, K):
+    """fused W4A16 tcgen05 GEMM (nibbles expanded to fp16(q * scale) by converter warps inside the kernel) against
+    the oracle's definition; the operand values are bit-identical, only the fp32 accumulation order differs"""
+    from oracle.weights import quantize_weight_w4
+    rng = np.random.default_rng(M + N + K)
+    w = (0.02 * rng.standard_normal((N, K))).astype(np.float16)
+    a = rng.standard_normal((M, K)).astype(np.float16)
+    q, s16, deq = quantize_weight_w4(w)
+    packed = torch.zeros((N, K // 2), dtype=torch.uint8, device="cuda")
+    scale = torch.zeros((N, K // 128), dtype=torch.float16, device="cuda")
+    capi.check(lib.b2llm_op_quant_weight_w4(stream_ptr(), _ptr(dev(w)), N, K, _ptr(packed), _ptr(scale)))
+    out = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+    capi.check(lib.b2llm_op_gemm_w4a16(stream_ptr(), _ptr(dev(a)), _ptr(packed), _ptr(scale), M, N, K, capi.EPI_F16, _ptr(out)))
+    sync()
+    exp = ref.gemm_f16_acc(a, deq)
+    got = out.cpu().numpy().astype(np.float32)
+    assert np.abs(got - exp).max() <= 1e-3 * np.abs(exp).max() + 1e-3   # fp16 output rounding (2^-11 relative)
+    # residual and SwiGLU epilogues
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    out2 = dev(res.copy())
+    capi.check(lib.b2llm_op_gemm_w4a16(stream_ptr(), _ptr(dev(a)), _ptr(packed), _ptr(scale), M, N, K, capi.EPI_RESIDUAL, _ptr(out2)))
+    out3 = torch.zeros((M, N // 2), dtype=torch.float16, device="cuda")
+    capi.check(lib.b2llm_op_gemm_w4a16(stream_ptr(), _ptr(dev(a)), _ptr(packed), _ptr(scale), M, N, K, capi.EPI_SWIGLU, _ptr(out3)))
+    sync()
+    exp2 = res.astype(np.float32) + exp
+    assert np.abs(out2.cpu().numpy().astype(np.float32) - exp2).max() <= 1e-3 * np.abs(exp2).max() + 2e-3
+    exp3 = ref.silu_mul(exp[:, 0::2], exp[:, 1::2])
+    np.testing.assert_allclose(out3.cpu().numpy().astype(np.float32), exp3, rtol=3e-3, atol=2e-3)
+
+
 @pytest.mark.parametrize("rows,hidden", [(1, 256), (37, 4096), (5, 5120), (3, 11008)])
 def test_rmsnorm_quant(lib, rows, hidden):
     rng = np.random.default_rng(rows * 7 + hidden)
