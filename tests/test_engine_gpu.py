@@ -226,6 +226,7 @@ def test_full_size_paging_invariance_and_split_modes():
         scale = res.kv_scale_mem.view(2 * H, T, D // 8)
         cache.index_copy_(1, slot, logical)
         scale.index_copy_(1, slot, logical_s)
+        torch.cuda.synchronize()  # the scatter ran on torch's stream, the engine has its own
         mi = ModelInput(token_inputs=tokens, seq_starts=np.arange(B + 1, dtype=np.int64), kv_starts=np.arange(B + 1, dtype=np.int64) * KV,
                         start_pos=np.full(B, KV - 1, dtype=np.int64), page_list=page_list.reshape(-1), max_pages=KV // PAGE,
                         decoding_batches=B, max_seq_len=1, max_kv_len=KV, temperatures=[1.0] * B, top_p_list=[0.0] * B,
@@ -237,15 +238,20 @@ def test_full_size_paging_invariance_and_split_modes():
             out.Resize(B)
             rc, err = engine.Execute(mi, True, False, out)
             assert rc == RC_SUCCESS, err
-            per_mode.append((engine.logits(B), out.output_token.copy()))
+            per_mode.append((engine.logits(B), out.output_token.copy(), engine.debug_read(2, (B, H * D), np.float16).astype(np.float32)))
         capi.check(res.lib.b2llm_engine_configure(res.engine, 3, 1), "configure split-k")
         outs.append(per_mode)
-    (la, ta), (lb, tb) = outs[0][0], outs[1][0]
+    (la, ta, aa), (lb, tb, ab) = outs[0][0], outs[1][0]
     assert np.isfinite(la).all()
     assert np.array_equal(la, lb) and np.array_equal(ta, tb), "logits depend on the physical page placement"
     assert np.array_equal(la[0], la[1]) and ta[0] == ta[1], "identical sequences gave different rows"
-    for l_mode, t_mode in outs[0][1:]:
-        rel = np.abs(l_mode - la).max(axis=1) / np.abs(la).max(axis=1)
-        # different split counts change only the fp32 merge order; a one-ulp flip of a W8A8 row max is possible but rare
-        assert np.median(rel) <= 1e-5 and (rel <= 1e-3).mean() >= 0.99, (np.median(rel), rel.max())
+    # split-k off == heuristic at this size (the grid alone fills the machine: one split) -> bit-identical
+    l0, t0, a0 = outs[0][1]
+    assert np.array_equal(l0, la) and np.array_equal(a0, aa)
+    # "always split": two partials merged in fp32 -> attention outputs within one fp16 ulp; through W8A8 a one-ulp
+    # move of a row re-scales its int8 codes, so logits are compared loosely and tokens by agreement rate
+    l2, t2, a2 = outs[0][2]
+    assert np.abs(a2 - aa).max() <= 2e-3 * max(1.0, np.abs(aa).max())
+    rel = np.abs(l2 - la).max(axis=1) / np.abs(la).max(axis=1)
+    assert rel.max() <= 0.1 and (t2 == ta).mean() >= 0.95, (rel.max(), (t2 == ta).mean())
     res.close()

@@ -195,3 +195,40 @@ def test_reference_generator_tensor_parallel_2(tmp_path):
                 break
             step = ref.build_step(desc, [[t]], [pos], 1, **kw)
             pos += 1
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_generator_with_penalty(tmp_path):
+    """--enable-penalty through the reference's own post-processor (post_processor.cc:221-281 -> pmx::apply_penalty ->
+    b2llm_apply_penalty): repetition penalty 1.3, greedy; batch slots come from the reference's IndexManager over the
+    CompactAddrManager stand-in.  Compared with the oracle's apply_penalty + arg-max chain per request."""
+    desc = ModelDesc(256, 512, 2, 4, 4, 512, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=128)
+    weights = SynthWeights(desc, 0xB200)
+    mdir = write_model_dir(tmp_path / "model", desc, seed=0xB200)
+    rng = np.random.default_rng(31)
+    reqs = [(i, 8, list(map(int, rng.integers(0, desc.vocab_size, n)))) for i, n in enumerate((5, 12, 3))]
+    (tmp_path / "req.txt").write_text("".join(f"{i} {g} {' '.join(map(str, p))}\n" for i, g, p in reqs))
+    r = _run([DRIVER, "--model-dir", mdir, "--requests-file", tmp_path / "req.txt", "--out", tmp_path / "out.txt",
+              "--max-running-batch", 8, "--max-tokens-per-step", 64, "--max-tokens-scale", 0.01, "--enable-penalty", 1,
+              "--repetition-penalty", 1.3])
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = {int(l.split()[0]): list(map(int, l.split()[1:])) for l in (tmp_path / "out.txt").read_text().splitlines()}
+    for i, g, p in reqs:
+        orc = ref.LlamaOracle(desc, weights, 32)
+        kw = dict(page_tables=[[0, 16]])
+        step = ref.build_step(desc, [p], [0], 0, **kw)
+        count_map = np.zeros((1, desc.vocab_size), np.uint16)
+        pos, inputs = len(p), list(p)
+        for k in range(g):
+            logits = orc.forward(step)
+            sp = 0 if k == 0 else pos - 1
+            sampler_ref.apply_penalty(logits, [1.0], [1.3], None, None, [0], inputs, [0, len(inputs)], [sp], desc.vocab_size, count_map)
+            t = int(logits[0].argmax())
+            top2 = np.sort(logits[0])[-2:]
+            if got[i][k] != t:
+                assert (top2[1] - top2[0]) / np.abs(logits[0]).max() < 2e-3, (i, k, got[i], t)
+                break
+            inputs = [t]
+            step = ref.build_step(desc, [[t]], [pos], 1, **kw)
+            pos += 1
