@@ -232,3 +232,43 @@ def test_reference_generator_with_penalty(tmp_path):
             inputs = [t]
             step = ref.build_step(desc, [[t]], [pos], 1, **kw)
             pos += 1
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_generator_prefix_cache_hit(tmp_path):
+    """--enable-prefix-cache: the reference's PrefixCacheManager / HashCombine page hashing decide the
+    hit; the second request then prefills only its tail with start_pos = 32 and ENGINE_CONF_CACHE_PREFILL = 1, so its
+    attention reads the first two pages (written by request 0) from the int8 cache.  The oracle replays exactly that."""
+    desc = ModelDesc(512, 1024, 2, 4, 4, 1024, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=256)
+    weights = SynthWeights(desc, 0xB200)
+    mdir = write_model_dir(tmp_path / "model", desc, seed=0xB200)
+    rng = np.random.default_rng(41)
+    shared = list(map(int, rng.integers(0, desc.vocab_size, 40)))
+    p0 = shared + list(map(int, rng.integers(0, desc.vocab_size, 5)))
+    p1 = shared + list(map(int, rng.integers(0, desc.vocab_size, 9)))
+    gen = 4
+    (tmp_path / "req.txt").write_text(f"0 {gen} {' '.join(map(str, p0))}\n1 {gen} {' '.join(map(str, p1))}\n")
+    r = _run([DRIVER, "--model-dir", mdir, "--requests-file", tmp_path / "req.txt", "--out", tmp_path / "out.txt",
+              "--max-running-batch", 8, "--max-tokens-per-step", 256, "--max-tokens-scale", 0.01, "--enable-prefix-cache", 1],
+             log="INFO")
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "Cache Hit [32]" in r.stderr, "the reference's prefix cache did not report the expected 2-page hit"
+    got = {int(l.split()[0]): list(map(int, l.split()[1:])) for l in (tmp_path / "out.txt").read_text().splitlines()}
+    orc = ref.LlamaOracle(desc, weights, 256)
+    pt0, pt1 = [0, 16, 32, 48], [0, 16, 64, 80]          # request 1 shares request 0's first two pages
+
+    def decode(tokens_so_far, first_logits, pt):
+        toks, logits, pos = [], first_logits, len(tokens_so_far)
+        for _ in range(gen):
+            t = int(logits[0].argmax())
+            toks.append(t)
+            logits = orc.forward(ref.build_step(desc, [[t]], [pos], 1, page_tables=[pt]))
+            pos += 1
+        return toks
+
+    l0 = orc.forward(ref.build_step(desc, [p0], [0], 0, page_tables=[pt0]))
+    l1 = orc.forward(ref.build_step(desc, [p1[32:]], [32], 0, page_tables=[pt1]))   # tail only, prefix from the cache
+    want0, want1 = decode(p0, l0, pt0), decode(p1, l1, pt1)
+    assert got[0] == want0
+    assert got[1] == want1
