@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--kv-len", type=int, default=0, help="override the fitted uniform KV length")
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kv-budget-tokens", type=int, default=0,
+                    help="allocate exactly this many KV tokens instead of the reference's 0.94 x free-memory budget "
+                         "(profiling runs: ncu saves / restores all device memory on every replay pass)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -201,7 +204,7 @@ def main():
     cfg.num_layers = args.layers
     res = CudaResourceManager()
     rc = res.Init(cfg, MAX_TOKENS_SCALE, max_running_batch=BATCH, max_tokens_per_step=BATCH, enable_penalty=False,
-                  kv_cache_max_tokens=None, seed=0xB200, device=local_rank)
+                  kv_cache_max_tokens=args.kv_budget_tokens or None, seed=0xB200, device=local_rank)
     if rc != RC_SUCCESS:
         raise SystemExit(f"engine init failed: {capi.load_library().b2llm_last_error().decode()}")
     lib = res.lib
