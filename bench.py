@@ -31,7 +31,14 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "decode tokens/sec (whole box) LLaMA-7B W8A8 batch1024 seq2048"
+def _baseline_metric():
+    try:
+        return json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+    except Exception:
+        return "decode tokens/sec (whole box) LLaMA-7B W8A8 batch1024 seq2048 @1/2/4/8 B200"
+
+
+METRIC = _baseline_metric()
 UNIT = "tokens/s"
 BATCH = 1024
 PAGE = 16
@@ -150,7 +157,7 @@ def reference_arm(args, kv_len):
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_time * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int8 (W8A8, int32 accumulate) / fp32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"LLaMA-2-7B W8A8 decode step, uniform kv_len {kv_len}, page_size {PAGE}, CPU sample batch {batch}"},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"batch {batch} of {BATCH}, 1- and 2-layer runs timed, per-layer {per_layer * 1e3:.1f} ms x 32 + head "
@@ -308,8 +315,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 (W8A8, int32 accumulate; int8 KV) / fp16 activations", "data": "synthetic",
+            "dtype": "int8", "data": "synthetic",
             "config": {
+                "arithmetic": "W8A8: int8 x int8 -> int32 tensor-core GEMMs, int8 group-8 KV cache, fp16 activations, fp32 reductions",
                 "workload": f"LLaMA-2-7B W8A8 TP=1, running batch {BATCH}, uniform kv_len {kv_len} "
                             f"(largest that fits: KV budget {max_tokens} tokens at max_tokens_scale {MAX_TOKENS_SCALE}; "
                             f"literal seq 2048 needs 687 GB), int8 group-8 paged KV page_size {PAGE} layout 3, greedy",
@@ -321,7 +329,7 @@ def main():
                 "device_ms_by_class_per_step": {"attention": ms_cls[0] / args.steps, "layer_gemms": ms_cls[1] / args.steps,
                                                 "lm_head": ms_cls[2] / args.steps},
             },
-            "roofline": {"kernel": "attn_decode_mma_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"kernel": "attn_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                          # exact shape (profiles/r1_ncu_attn.txt); null for any other shape

@@ -820,7 +820,8 @@ int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* pac
     }
     if (M == 0) return B2LLM_OK;
     const __half* sc = (const __half*)scale_fp16;
-    const bool two = M > BM;
+    // two A tiles per weight tile halve the conversion work, but only pay once the grid still fills half the machine
+    const bool two = M > BM && ((M + 2 * BM - 1) / (2 * BM)) * (N / W4_BN) >= gemm_sm_budget() / 2;
     switch (epilogue) {
         case EPI_F16: return two ? launch_w4<EPI_F16, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_F16, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
         case EPI_RESIDUAL: return two ? launch_w4<EPI_RESIDUAL, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_RESIDUAL, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
