@@ -150,6 +150,166 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const __half* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident row kernels.  The CTA-per-row kernels above re-read the row for every pass and synchronise
+// the block four times; at 1024 rows x 4096 columns that costs ~11 us for 12 MB (profiles/r1_ncu_full_step_run11.txt).
+// Here W warps own one row (W = 1: no block synchronisation at all), every lane keeps its V 16-byte vectors of the
+// row in registers across the passes, and reductions are warp shuffles (+ one shared-memory exchange when W > 1).
+// Same arithmetic, same fp64 variance, same rounding points as the kernels above -> bit-identical results.
+template <int W>
+__device__ __forceinline__ float rowgroup_max(float v, float* scratch, int w) {
+    v = warp_max(v);
+    if constexpr (W > 1) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) scratch[w] = v;
+        __syncthreads();
+        v = scratch[0];
+#pragma unroll
+        for (int i = 1; i < W; ++i) v = fmaxf(v, scratch[i]);
+    }
+    return v;
+}
+template <int W>
+__device__ __forceinline__ double rowgroup_sum_f64(double v, double* scratch, int w) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if constexpr (W > 1) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) scratch[w] = v;
+        __syncthreads();
+        v = scratch[0];
+#pragma unroll
+        for (int i = 1; i < W; ++i) v += scratch[i];
+    }
+    return v;
+}
+
+// V vectors per lane, W warps per row.  W == 1: a 128-thread CTA handles 4 rows; W > 1: a CTA of W warps handles one row.
+template <int V, int W, bool NORM>
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W)
+    row_quant_reg_kernel(__half* __restrict__ x, const __half* __restrict__ skip, const __half* __restrict__ gamma, float eps,
+                         int64_t rows, int cols, int8_t* __restrict__ q, float* __restrict__ scale, __half* __restrict__ y_out) {
+    __shared__ float fscratch[W > 1 ? W : 1];
+    __shared__ double dscratch[W > 1 ? W : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = W == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x;
+    const int w = W == 1 ? 0 : warp;
+    if (row >= rows) return;  // W == 1 only: whole warps leave, no block-level sync is used in that configuration
+    const int nvec = cols >> 3;
+    __half* xr = x + row * cols;
+    Half8 a[V];
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int v = i * (32 * W) + w * 32 + lane;
+        if (v < nvec) {
+            a[i] = ld8(xr + v * 8);
+            if constexpr (NORM) {
+                if (skip != nullptr) {
+                    const Half8 b = ld8(skip + row * cols + v * 8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 fa = __half22float2(a[i].v[j]), fb = __half22float2(b.v[j]);
+                        a[i].v[j] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+                    }
+                    st8(xr + v * 8, a[i]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(a[i].v[j]);
+                    ss += (double)f.x * (double)f.x + (double)f.y * (double)f.y;
+                }
+            }
+        }
+    }
+    float inv = 1.f;
+    if constexpr (NORM) {
+        ss = rowgroup_sum_f64<W>(ss, dscratch, w);
+        const float var = (float)(ss / (double)cols);
+        inv = __fdiv_rn(1.0f, sqrtf(__fadd_rn(var, eps)));
+    }
+    // y = (x * inv) * gamma kept as fp32 pairs only transiently: recomputed per pass from the register-resident x
+    auto yv = [&](const Half8& xa, const Half8& g, int j) -> float2 {
+        const float2 fa = __half22float2(xa.v[j]);
+        if constexpr (NORM) {
+            const float2 fg = __half22float2(g.v[j]);
+            return make_float2(__fmul_rn(__fmul_rn(fa.x, inv), fg.x), __fmul_rn(__fmul_rn(fa.y, inv), fg.y));
+        } else {
+            return fa;
+        }
+    };
+    if (NORM && q == nullptr) {  // plain fp16 output
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int v = i * (32 * W) + w * 32 + lane;
+            if (v < nvec) {
+                const Half8 g = ld8(gamma + v * 8);
+                Half8 o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = yv(a[i], g, j);
+                    o.v[j] = __floats2half2_rn(f.x, f.y);
+                }
+                st8(y_out + row * cols + v * 8, o);
+            }
+        }
+        return;
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int v = i * (32 * W) + w * 32 + lane;
+        if (v < nvec) {
+            Half8 g;
+            if constexpr (NORM) g = ld8(gamma + v * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = yv(a[i], g, j);
+                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+            }
+        }
+    }
+    amax = rowgroup_max<W>(amax, fscratch, w);
+    const float inv_scale = amax > 0.f ? __fdiv_rn(127.0f, amax) : 0.f;
+    if (lane == 0 && w == 0) scale[row] = __fdiv_rn(amax, 127.0f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int v = i * (32 * W) + w * 32 + lane;
+        if (v < nvec) {
+            Half8 g;
+            if constexpr (NORM) g = ld8(gamma + v * 8);
+            uint32_t wd[2] = {0, 0};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = yv(a[i], g, j);
+                wd[j >> 1] |= (uint32_t)(q8(f.x, inv_scale) & 0xff) << (16 * (j & 1));
+                wd[j >> 1] |= (uint32_t)(q8(f.y, inv_scale) & 0xff) << (16 * (j & 1) + 8);
+            }
+            *reinterpret_cast<uint2*>(q + row * cols + v * 8) = make_uint2(wd[0], wd[1]);
+        }
+    }
+}
+
+template <bool NORM>
+bool launch_row_reg(cudaStream_t s, __half* x, const __half* skip, const __half* gamma, float eps, int64_t rows, int cols,
+                    int8_t* q, float* scale, __half* y) {
+    const int nvec = cols >> 3;
+    const int W = nvec <= 1024 ? 1 : (nvec <= 2048 ? 2 : 4);
+    const int need = (nvec + 32 * W - 1) / (32 * W);
+    if (need > 32) return false;  // > 32768 columns: CTA-per-row kernel
+    const unsigned blocks = W == 1 ? (unsigned)((rows + 3) / 4) : (unsigned)rows;
+#define B2_ROW_LAUNCH(VV, WW) row_quant_reg_kernel<VV, WW, NORM><<<blocks, WW == 1 ? 128 : 32 * WW, 0, s>>>(x, skip, gamma, eps, rows, cols, q, scale, y)
+#define B2_ROW_V(WW)                                           \
+    if (need <= 8) B2_ROW_LAUNCH(8, WW);                       \
+    else if (need <= 16) B2_ROW_LAUNCH(16, WW);                \
+    else if (need <= 24) B2_ROW_LAUNCH(24, WW);                \
+    else B2_ROW_LAUNCH(32, WW)
+    if (W == 1) { B2_ROW_V(1); } else if (W == 2) { B2_ROW_V(2); } else { B2_ROW_V(4); }
+#undef B2_ROW_V
+#undef B2_ROW_LAUNCH
+    return true;
+}
+
 // out[i, :] = table[ids[i], :]
 __global__ void embedding_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ table, int hidden, int vocab,
                                  __half* __restrict__ out) {
@@ -169,6 +329,15 @@ __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* 
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + b * hidden + v * 8, ld8(x + t * hidden + v * 8));
 }
 
+// B2LLM_ROW_KERNELS=legacy selects the CTA-per-row kernels (cross-check / A-B timing)
+bool row_kernels_legacy() {
+    static const bool legacy = [] {
+        const char* e = getenv("B2LLM_ROW_KERNELS");
+        return e != nullptr && e[0] == 'l';
+    }();
+    return legacy;
+}
+
 }  // namespace
 
 int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, const __half* gamma, float eps, int64_t rows,
@@ -176,6 +345,10 @@ int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, cons
     B2_REQUIRE(hidden % 8 == 0, B2LLM_ERR_INVALID_VALUE, "rmsnorm: hidden must be a multiple of 8");
     B2_REQUIRE((q != nullptr && scale != nullptr) || y != nullptr, B2LLM_ERR_INVALID_VALUE, "rmsnorm: no output");
     if (rows == 0) return B2LLM_OK;
+    if (!row_kernels_legacy() && launch_row_reg<true>(s, x, skip, gamma, eps, rows, hidden, q, scale, y)) {
+        B2_LAUNCH_CHECK();
+        return B2LLM_OK;
+    }
     rmsnorm_quant_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, skip, gamma, eps, hidden, q, scale, y);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
@@ -184,6 +357,10 @@ int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, cons
 int32_t launch_quant_rows(cudaStream_t s, const __half* x, int64_t rows, int cols, int8_t* q, float* scale) {
     B2_REQUIRE(cols % 8 == 0, B2LLM_ERR_INVALID_VALUE, "quant_rows: cols must be a multiple of 8");
     if (rows == 0) return B2LLM_OK;
+    if (!row_kernels_legacy() && launch_row_reg<false>(s, const_cast<__half*>(x), nullptr, nullptr, 0.f, rows, cols, q, scale, nullptr)) {
+        B2_LAUNCH_CHECK();
+        return B2LLM_OK;
+    }
     quant_rows_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, cols, q, scale);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
