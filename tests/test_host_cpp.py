@@ -49,6 +49,27 @@ def test_host_library_exports_plugin_surface():
         assert want in syms, f"libpplnn_b200.so does not define {want}"
 
 
+def test_ppl_common_standin_unit_tests():
+    """PageManager, CompactAddrManager, MPSCQueue / TypedMPSCQueue (4 producers), StaticThreadPool (thread i == index i),
+    Barrier, EventCount (no lost wake-up): C++ unit tests of host/include/ppl/common, CPU only"""
+    exe = ROOT / "ppl.llm.serving_b200" / "host" / "build" / "test_ppl_common"
+    assert exe.exists(), "build with `python __graft_entry__.py build`"
+    r = _run([exe], timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all ok" in r.stdout
+
+
+def test_ppl_common_standin_under_thread_sanitizer():
+    """the same C++ unit tests built with -fsanitize=thread: no data race in the MPSC queue, EventCount, thread pool"""
+    host = ROOT / "ppl.llm.serving_b200" / "host"
+    b = subprocess.run(["make", "-C", str(host), "build/test_ppl_common_tsan"], capture_output=True, text=True, timeout=300)
+    if b.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available: " + b.stderr[-300:])
+    r = subprocess.run([str(host / "build" / "test_ppl_common_tsan")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66"))
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]
+
+
 @needs_ref
 def test_reference_tools_link_and_fail_loudly_without_gpu(tmp_path):
     import torch
