@@ -158,7 +158,9 @@ def reference_arm(args, kv_len):
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_time * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": f"LLaMA-2-7B W8A8 decode step, uniform kv_len {kv_len}, page_size {PAGE}, CPU sample batch {batch}"},
+        "config": {"workload": f"LLaMA-2-7B W8A8 TP=1, running batch {BATCH}, uniform kv_len {kv_len} (the length the b200 arm fits on "
+                               f"one 180 GB B200 at max_tokens_scale {MAX_TOKENS_SCALE}), int8 group-8 paged KV page_size {PAGE} layout 3, "
+                               f"greedy; CPU arm measured on a batch-{batch} sample of this step (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"batch {batch} of {BATCH}, 1- and 2-layer runs timed, per-layer {per_layer * 1e3:.1f} ms x 32 + head "
                                    f"{head * 1e3:.1f} ms; numpy/BLAS on all {cores} host threads; the reference has no CPU "
@@ -185,7 +187,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
-        reference_arm(args, args.kv_len or 496)
+        reference_arm(args, args.kv_len or 512)
         return
 
     # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
