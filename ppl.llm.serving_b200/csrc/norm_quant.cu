@@ -294,13 +294,17 @@ template <bool NORM>
 bool launch_row_reg(cudaStream_t s, __half* x, const __half* skip, const __half* gamma, float eps, int64_t rows, int cols,
                     int8_t* q, float* scale, __half* y) {
     const int nvec = cols >> 3;
-    const int W = nvec <= 1024 ? 1 : (nvec <= 2048 ? 2 : 4);
+    // warps per row: enough rows-in-flight parallelism matters more than avoiding the block sync -- one warp per
+    // 4096-column row measured SLOWER in the step than the CTA-per-row kernels (run 12: 7 warps per SM, long dependent
+    // chains), so wide rows are spread over 4 warps
+    const int W = nvec < 256 ? 1 : (nvec < 512 ? 2 : 4);
     const int need = (nvec + 32 * W - 1) / (32 * W);
     if (need > 32) return false;  // > 32768 columns: CTA-per-row kernel
     const unsigned blocks = W == 1 ? (unsigned)((rows + 3) / 4) : (unsigned)rows;
 #define B2_ROW_LAUNCH(VV, WW) row_quant_reg_kernel<VV, WW, NORM><<<blocks, WW == 1 ? 128 : 32 * WW, 0, s>>>(x, skip, gamma, eps, rows, cols, q, scale, y)
 #define B2_ROW_V(WW)                                           \
-    if (need <= 8) B2_ROW_LAUNCH(8, WW);                       \
+    if (need <= 4) B2_ROW_LAUNCH(4, WW);                       \
+    else if (need <= 8) B2_ROW_LAUNCH(8, WW);                  \
     else if (need <= 16) B2_ROW_LAUNCH(16, WW);                \
     else if (need <= 24) B2_ROW_LAUNCH(24, WW);                \
     else B2_ROW_LAUNCH(32, WW)
@@ -329,11 +333,12 @@ __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* 
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + b * hidden + v * 8, ld8(x + t * hidden + v * 8));
 }
 
-// B2LLM_ROW_KERNELS=legacy selects the CTA-per-row kernels (cross-check / A-B timing)
+// The CTA-per-row kernels are the default; B2LLM_ROW_KERNELS=reg selects the register-resident variants (bit-identical
+// results, tests/test_ops_gpu.py ran green on them in run 12; not yet faster in the step)
 bool row_kernels_legacy() {
     static const bool legacy = [] {
         const char* e = getenv("B2LLM_ROW_KERNELS");
-        return e != nullptr && e[0] == 'l';
+        return !(e != nullptr && e[0] == 'r');
     }();
     return legacy;
 }
