@@ -77,3 +77,27 @@ def test_engine_create_fails_loudly_without_gpu(lib):
 def test_missing_library_raises():
     with pytest.raises(capi.B2llmError, match="no fallback"):
         capi.load_library("/nonexistent/libb2llm.so")
+
+
+def test_argument_validation_precedes_device_work(lib):
+    """error behaviour of the boundary: RetCode values, never exceptions or crashes; null / malformed
+    arguments are rejected before any CUDA call, so this runs without a GPU"""
+    P = C.c_void_p
+    assert lib.b2llm_op_rmsnorm_quant(None, None, None, None, 1e-5, 4, 256, None, None, None) == 2
+    assert lib.b2llm_op_quant_rows(None, None, 4, 256, None, None) == 2
+    assert lib.b2llm_op_gemm_w8a8(None, None, None, None, None, 4, 256, 256, 0, None, 0) == 2
+    one = (C.c_byte * 16)()
+    p = C.cast(one, P)
+    assert lib.b2llm_op_gemm_w8a8(None, p, p, p, p, 4, 256, 256, 7, p, 0) == 2          # unknown epilogue
+    assert lib.b2llm_op_gemm_f16(None, None, None, 4, 256, 256, 0, None, 0, 0) == 2
+    assert lib.b2llm_op_gemm_w4a16(None, None, None, None, 4, 256, 256, 0, None) == 2
+    assert lib.b2llm_op_attention(None, None, None, 4, None, 0, None, None, None, None, 0) == 2
+    assert lib.b2llm_op_rope_kv_append(None, None, None, 4, None, 0, None, None, None, None) == 2
+    assert lib.b2llm_engine_set_inputs(None, None, 0, None, None, None, 0, None, 0, 0, 0, 0, 0) == 2
+    assert lib.b2llm_engine_forward(None, None, None, None) == 2
+    assert lib.b2llm_engine_bind_kv(None, None, None, 0) == 2
+    assert lib.b2llm_engine_reserve(None, 1, 1) == 2
+    assert lib.b2llm_engine_configure(None, 3, 1) == 2
+    assert lib.b2llm_engine_destroy(None) == 0                                          # destroying nothing is fine
+    assert lib.b2llm_engine_last_launch_count(None) == 0
+    assert lib.b2llm_last_error()                                                        # text of the last failure
