@@ -151,6 +151,12 @@ B2LLM_API int32_t b2llm_engine_configure(b2llm_engine* e, int32_t key, int64_t v
  * random_init fills every weight with the seeded synthetic generator. */
 B2LLM_API int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
                                            uint64_t num_elements);
+/* same, but the host tensor already is THIS RANK's tensor-parallel shard, as a ppl.pmx export stores it in
+ * model_slice_<rank>/model.onnx (resource_manager.cc:280-286; docs/llama_guide.md:14-36): QKV fp16
+ * [(nq/tp + 2 nkv/tp) * head_dim, hidden] (local q heads, k heads, v heads), O [hidden, nq/tp * head_dim],
+ * GATE / UP [intermediate/tp, hidden], DOWN [hidden, intermediate/tp]; embedding, lm_head and the norms are whole. */
+B2LLM_API int32_t b2llm_engine_load_weight_shard(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
+                                                 uint64_t num_elements);
 B2LLM_API int32_t b2llm_engine_random_init(b2llm_engine* e, uint64_t seed);
 
 /* KV memory is owned by the caller (resource_manager.cc:344-362 cudaMalloc's it and

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2llm_engine_reserve": (_I32, [_P, _I64, _I64]),
     "b2llm_engine_configure": (_I32, [_P, _I32, _I64]),
     "b2llm_engine_load_weight": (_I32, [_P, _I32, _I32, _P, _U64]),
+    "b2llm_engine_load_weight_shard": (_I32, [_P, _I32, _I32, _P, _U64]),
     "b2llm_engine_random_init": (_I32, [_P, _U64]),
     "b2llm_engine_bind_kv": (_I32, [_P, _P, _P, _U64]),
     "b2llm_engine_kv_bytes_per_token": (_I32, [_P, C.POINTER(_U64), C.POINTER(_U64)]),

@@ -444,13 +444,18 @@ int32_t finish_gate_up(b2llm_engine* e, Layer& L) {
 
 }  // namespace
 
-extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
-                                            uint64_t num_elements) {
+namespace {
+// `sharded`: the host tensor already is this rank's tensor-parallel shard (what a ppl.pmx export stores per
+// model_slice_<rank>); otherwise it is the full tensor and the rank's window is cut out here.
+int32_t load_weight_impl(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16, uint64_t num_elements,
+                         bool sharded) {
     B2_REQUIRE(e && host_fp16, B2LLM_ERR_INVALID_VALUE, "load_weight: null argument");
     const b2llm_model_desc& d = e->d;
     const __half* src = (const __half*)host_fp16;
     const int64_t h = d.hidden_dim, D = e->D;
-    const int r = e->rank;
+    const int r = sharded ? 0 : e->rank;
+    const int64_t NQ = sharded ? e->nq : d.num_heads, NKV = sharded ? e->nkv : d.num_kv_heads;
+    const int64_t I = sharded ? e->inter : d.intermediate_dim;
     auto expect = [&](uint64_t n) -> bool {
         if (num_elements != n) {
             set_last_error("load_weight: expected " + std::to_string(n) + " elements, got " + std::to_string(num_elements));
@@ -484,7 +489,6 @@ extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32
             break;
         }
         case B2LLM_W_QKV: {
-            const int64_t NQ = d.num_heads, NKV = d.num_kv_heads;
             if (!expect((uint64_t)((NQ + 2 * NKV) * D * h))) return B2LLM_ERR_INVALID_VALUE;
             if ((rc = stage.ensure((size_t)e->nqkv * h * 2))) return rc;
             __half* s16 = stage.as<__half>();
@@ -496,7 +500,7 @@ extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32
             break;
         }
         case B2LLM_W_O: {
-            const int64_t full = (int64_t)d.num_heads * D;
+            const int64_t full = NQ * D;
             if (!expect((uint64_t)(h * full))) return B2LLM_ERR_INVALID_VALUE;
             if ((rc = stage.ensure((size_t)h * e->nq * D * 2))) return rc;
             rc = upload_window(e, src, full, 0, h, (int64_t)r * e->nq * D, e->nq * D, stage.as<__half>());
@@ -505,7 +509,7 @@ extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32
         }
         case B2LLM_W_GATE:
         case B2LLM_W_UP: {
-            if (!expect((uint64_t)d.intermediate_dim * h)) return B2LLM_ERR_INVALID_VALUE;
+            if (!expect((uint64_t)I * h)) return B2LLM_ERR_INVALID_VALUE;
             DevBuf& dst = kind == B2LLM_W_GATE ? L.gate_stage : L.up_stage;
             if ((rc = dst.ensure((size_t)e->inter * h * 2))) return rc;
             rc = upload_window(e, src, h, (int64_t)r * e->inter, e->inter, 0, h, dst.as<__half>());
@@ -514,7 +518,7 @@ extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32
             break;
         }
         case B2LLM_W_DOWN: {
-            const int64_t full = d.intermediate_dim;
+            const int64_t full = I;
             if (!expect((uint64_t)(h * full))) return B2LLM_ERR_INVALID_VALUE;
             if ((rc = stage.ensure((size_t)h * e->inter * 2))) return rc;
             rc = upload_window(e, src, full, 0, h, (int64_t)r * e->inter, e->inter, stage.as<__half>());
@@ -532,6 +536,17 @@ extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32
         rc = B2LLM_ERR_DEVICE;
     }
     return rc;
+}
+}  // namespace
+
+extern "C" int32_t b2llm_engine_load_weight(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
+                                            uint64_t num_elements) {
+    return load_weight_impl(e, kind, layer, host_fp16, num_elements, false);
+}
+
+extern "C" int32_t b2llm_engine_load_weight_shard(b2llm_engine* e, int32_t kind, int32_t layer, const void* host_fp16,
+                                                  uint64_t num_elements) {
+    return load_weight_impl(e, kind, layer, host_fp16, num_elements, true);
 }
 
 extern "C" int32_t b2llm_engine_random_init(b2llm_engine* e, uint64_t seed) {

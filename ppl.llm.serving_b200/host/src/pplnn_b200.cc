@@ -7,14 +7,16 @@
 // UNCHANGED against libb2llm.so instead of ppl.nn + ppl.llm.kernel.cuda.
 //
 //   EngineFactory::Create            -> B200Engine (options, NCCL communicator, Configure keys)
-//   RuntimeBuilder::LoadModel        -> parses a b2llm model-slice descriptor
-//   RuntimeBuilder::CreateRuntime    -> b2llm_engine_create + weights (synthetic seed or fp16 blob)
+//   RuntimeBuilder::LoadModel        -> reads model_slice_<rank>/model.onnx: a ppl.pmx ONNX export (onnx_model.cc,
+//                                       pmx_llama.cc) or a b2llm model-slice descriptor
+//   RuntimeBuilder::CreateRuntime    -> b2llm_engine_create + weights (ONNX initializers, synthetic seed or fp16 blob)
 //   Tensor::CopyFromHostAsync        -> cudaMemcpyAsync on the rank's stream (or host memcpy for the 3 scalars)
 //   Runtime::Run                     -> b2llm_engine_reserve + b2llm_engine_bind_kv + b2llm_engine_forward
 //
 // No computation happens here and nothing falls back to the CPU: without a B200 every entry point returns a
 // RetCode error.
 #include "b2llm.h"
+#include "pmx_llama.h"
 
 #include "ppl/common/log.h"
 #include "ppl/nn/engines/llm_cuda/engine_factory.h"
@@ -336,9 +338,32 @@ private:
 struct SliceDesc {
     b2llm_model_desc d{};
     int tp = 1, rank = 0;
-    std::string weights; // "synthetic:<seed>" or "file:<path relative to the descriptor>"
+    std::string weights; // "synthetic:<seed>", "file:<path relative to the descriptor>" or "onnx" (pmx below)
     std::string dir;
+    std::shared_ptr<b2onnx::PmxLlama> pmx; // the parsed ppl.pmx export when model.onnx is a real ONNX file
 };
+
+// model.onnx of a ppl.pmx export (docs/llama_guide.md:12-36): dimensions and constants from the graph, weights
+// from its initializers
+bool ParsePmxOnnx(const char* path, SliceDesc* out) {
+    std::shared_ptr<b2onnx::PmxLlama> pmx(new b2onnx::PmxLlama());
+    std::string err;
+    if (!pmx->Open(path, &err)) {
+        LOG(ERROR) << "model [" << path << "]: " << err;
+        return false;
+    }
+    for (const auto& w : pmx->warnings()) LOG(WARNING) << "model [" << path << "]: " << w;
+    out->d = pmx->desc();
+    out->tp = pmx->tensor_parallel_size();
+    out->rank = pmx->rank() < 0 ? 0 : pmx->rank();
+    out->weights = "onnx";
+    out->dir = pmx->model().dir;
+    out->pmx = pmx;
+    LOG(INFO) << "model [" << path << "]: pmx LLaMA export, producer [" << pmx->model().producer_name << "], "
+              << out->d.num_layers << " layers, hidden " << out->d.hidden_dim << ", heads " << out->d.num_heads << "/"
+              << out->d.num_kv_heads << ", tensor-parallel slice " << out->rank << " of " << out->tp;
+    return true;
+}
 
 bool ParseSlice(const char* path, SliceDesc* out) {
     std::ifstream ifs(path);
@@ -346,12 +371,15 @@ bool ParseSlice(const char* path, SliceDesc* out) {
         LOG(ERROR) << "model slice [" << path << "]: cannot open";
         return false;
     }
-    std::string line;
-    if (!std::getline(ifs, line) || line.rfind("b2llm-model-slice 1", 0) != 0) {
-        LOG(ERROR) << "model slice [" << path << "]: not a b2llm model-slice descriptor (ONNX graphs exported by ppl.pmx "
-                   << "are not read yet: SURVEY.md 8f row 2; see INTEGRATION.md section 4)";
-        return false;
+    char magic[20] = {0};
+    ifs.read(magic, 19);
+    if (strncmp(magic, "b2llm-model-slice 1", 19) != 0) {
+        ifs.close();
+        return ParsePmxOnnx(path, out); // a protobuf: the ppl.pmx export the reference's docs describe
     }
+    ifs.seekg(0);
+    std::string line;
+    std::getline(ifs, line);
     std::map<std::string, std::string> kv;
     while (std::getline(ifs, line)) {
         const auto hash = line.find('#');
@@ -608,6 +636,16 @@ public:
             rc = FromB2(b2llm_engine_random_init(e, strtoull(slice_.weights.c_str() + 10, nullptr, 0)), "b2llm_engine_random_init");
         } else if (slice_.weights.rfind("file:", 0) == 0) {
             rc = LoadWeightBlob(e, d, slice_.dir + "/" + slice_.weights.substr(5));
+        } else if (slice_.pmx) {
+            std::string err;
+            const int32_t brc = slice_.pmx->ForEachWeight(
+                [&](int32_t kind, int32_t layer, const void* fp16, uint64_t n, const char*) {
+                    return b2llm_engine_load_weight_shard(e, kind, layer, fp16, n);
+                },
+                &err);
+            if (brc != B2LLM_OK && !err.empty()) LOG(ERROR) << "model [" << slice_.pmx->model().path << "]: " << err;
+            rc = FromB2(brc, "loading the ONNX initializers (b2llm_engine_load_weight_shard)");
+            slice_.pmx.reset(); // unmap the export; the weights now live in HBM
         } else {
             LOG(ERROR) << "model slice: unknown weights source [" << slice_.weights << "]";
             rc = RC_INVALID_VALUE;

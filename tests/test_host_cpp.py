@@ -23,6 +23,7 @@ from oracle import llama_ref as ref
 from oracle import sampler_ref
 from oracle.weights import ModelDesc, SynthWeights
 from ppl_llm_serving_b200.model_slice import write_model_dir
+from ppl_llm_serving_b200.pmx_onnx_writer import write_pmx_export
 
 ROOT = Path(__file__).resolve().parent.parent
 REFDIR = ROOT / "oracle" / "_ref"
@@ -138,6 +139,72 @@ def test_reference_generator_over_b2llm_matches_oracle(tmp_path, quant, layout, 
                 # only an (algorithmic) near-tie may differ; everything after it diverges legitimately
                 assert margins[k] < 2e-3, f"request {i} token {k}: got {a}, oracle {b}, margin {margins[k]:.2e}"
                 break
+
+
+def _check_against_oracle(desc, weights, reqs, got, tp=1):
+    for i, g, p in reqs:
+        pages = (len(p) + g + desc.page_size - 1) // desc.page_size
+        orc = ref.LlamaOracle(desc, weights, pages * desc.page_size, tp=tp)
+        kw = dict(page_tables=[[k * desc.page_size for k in range(pages)]])
+        step = ref.build_step(desc, [p], [0], 0, **kw)
+        pos = len(p)
+        assert len(got[i]) == g
+        for k in range(g):
+            logits = orc.forward(step)
+            t = int(logits[0].argmax())
+            top2 = np.sort(logits[0])[-2:]
+            if got[i][k] != t:
+                assert (top2[1] - top2[0]) / np.abs(logits[0]).max() < 2e-3, (i, k, got[i], t)
+                break
+            step = ref.build_step(desc, [[t]], [pos], 1, **kw)
+            pos += 1
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("variant", ["fused_inline_fp16", "split_external_fp32"])
+def test_reference_generator_from_pmx_onnx_export(tmp_path, variant):
+    """model_slice_0/model.onnx is a real ONNX ModelProto in the layout of a ppl.pmx export
+    (docs/llama_guide.md:12-36) -- RuntimeBuilder::LoadModel reads dimensions / constants from the pmx nodes and the
+    weights from the initializers (b2llm_engine_load_weight_shard), --quant-method online_i8i8 quantises them at load
+    (resource_manager.cc:51-52).  GQA, 8 q heads over 2 kv heads; tokens must match the oracle holding the same weights."""
+    desc = ModelDesc(512, 1024, 2, 8, 2, 1024, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=256)
+    weights = SynthWeights(desc, 0x5EED)
+    if variant == "fused_inline_fp16":
+        mdir = write_pmx_export(tmp_path / "model", desc, weights)
+    else:
+        mdir = write_pmx_export(tmp_path / "model", desc, weights, fused_qkv=False, external_data=True, dtype="fp32", syntax="proto2")
+    rng = np.random.default_rng(29)
+    reqs = [(i, 5, list(map(int, rng.integers(0, desc.vocab_size, n)))) for i, n in enumerate((9, 26, 2))]
+    (tmp_path / "req.txt").write_text("".join(f"{i} {g} {' '.join(map(str, p))}\n" for i, g, p in reqs))
+    r = _run([DRIVER, "--model-dir", mdir, "--quant-method", "online_i8i8", "--requests-file", tmp_path / "req.txt",
+              "--out", tmp_path / "out.txt", "--max-running-batch", 8, "--max-tokens-per-step", 256,
+              "--max-tokens-scale", 0.01])
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = {int(l.split()[0]): list(map(int, l.split()[1:])) for l in (tmp_path / "out.txt").read_text().splitlines()}
+    _check_against_oracle(desc, weights, reqs, got)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_generator_from_pmx_onnx_export_tensor_parallel_2(tmp_path):
+    """two model slices as ppl.pmx writes them for MP = 2 (docs/llama_guide.md:27-36): column / row shards per rank, the
+    embedding split along hidden and the lm head along vocab (re-assembled at load)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    desc = ModelDesc(512, 1024, 2, 4, 2, 1024, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=256)
+    weights = SynthWeights(desc, 0x5EED)
+    mdir = write_pmx_export(tmp_path / "model", desc, weights, tensor_parallel_size=2)
+    rng = np.random.default_rng(37)
+    reqs = [(i, 5, list(map(int, rng.integers(0, desc.vocab_size, n)))) for i, n in enumerate((6, 21))]
+    (tmp_path / "req.txt").write_text("".join(f"{i} {g} {' '.join(map(str, p))}\n" for i, g, p in reqs))
+    r = _run([DRIVER, "--model-dir", mdir, "--tensor-parallel-size", 2, "--quant-method", "online_i8i8", "--requests-file",
+              tmp_path / "req.txt", "--out", tmp_path / "out.txt", "--max-running-batch", 8, "--max-tokens-per-step", 256,
+              "--max-tokens-scale", 0.01])
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = {int(l.split()[0]): list(map(int, l.split()[1:])) for l in (tmp_path / "out.txt").read_text().splitlines()}
+    _check_against_oracle(desc, weights, reqs, got, tp=2)
 
 
 @pytest.mark.gpu
