@@ -333,14 +333,15 @@ __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* 
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + b * hidden + v * 8, ld8(x + t * hidden + v * 8));
 }
 
-// The CTA-per-row kernels are the default; B2LLM_ROW_KERNELS=reg selects the register-resident variants (bit-identical
-// results, tests/test_ops_gpu.py ran green on them in run 12; not yet faster in the step)
-bool row_kernels_legacy() {
-    static const bool legacy = [] {
+// Which row kernel: CTA-per-row wins at decode sizes (rows = running batch ~ 1e3: run 12), the register-resident
+// warp-per-row variants at prefill sizes (65 536 rows: 74 vs 89 ms of norm / quant / rope time per 32-layer step, run 16).
+// Results are bit-identical.  B2LLM_ROW_KERNELS=reg / legacy forces one of them.
+bool use_row_reg(int64_t rows) {
+    static const int mode = [] {
         const char* e = getenv("B2LLM_ROW_KERNELS");
-        return !(e != nullptr && e[0] == 'r');
+        return e == nullptr ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'l' ? 2 : 0));
     }();
-    return legacy;
+    return mode == 1 || (mode == 0 && rows >= 8192);
 }
 
 }  // namespace
@@ -350,7 +351,7 @@ int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, cons
     B2_REQUIRE(hidden % 8 == 0, B2LLM_ERR_INVALID_VALUE, "rmsnorm: hidden must be a multiple of 8");
     B2_REQUIRE((q != nullptr && scale != nullptr) || y != nullptr, B2LLM_ERR_INVALID_VALUE, "rmsnorm: no output");
     if (rows == 0) return B2LLM_OK;
-    if (!row_kernels_legacy() && launch_row_reg<true>(s, x, skip, gamma, eps, rows, hidden, q, scale, y)) {
+    if (use_row_reg(rows) && launch_row_reg<true>(s, x, skip, gamma, eps, rows, hidden, q, scale, y)) {
         B2_LAUNCH_CHECK();
         return B2LLM_OK;
     }
@@ -362,7 +363,7 @@ int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, cons
 int32_t launch_quant_rows(cudaStream_t s, const __half* x, int64_t rows, int cols, int8_t* q, float* scale) {
     B2_REQUIRE(cols % 8 == 0, B2LLM_ERR_INVALID_VALUE, "quant_rows: cols must be a multiple of 8");
     if (rows == 0) return B2LLM_OK;
-    if (!row_kernels_legacy() && launch_row_reg<false>(s, const_cast<__half*>(x), nullptr, nullptr, 0.f, rows, cols, q, scale, nullptr)) {
+    if (use_row_reg(rows) && launch_row_reg<false>(s, const_cast<__half*>(x), nullptr, nullptr, 0.f, rows, cols, q, scale, nullptr)) {
         B2_LAUNCH_CHECK();
         return B2LLM_OK;
     }
