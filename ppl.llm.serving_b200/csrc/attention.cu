@@ -183,6 +183,19 @@ __device__ __forceinline__ void mma_f16_full(float (&d)[4], uint32_t a0, uint32_
 //     O^T[d, head]    += V^T[d, token] . P^T[token, head]    A = dequantised V (token pairs gathered by PRMT),
 //                                                            B = P moved from accumulator to operand layout
 //                                                                by movmatrix.trans, as hi + lo fp16 halves
+// ex2.approx.ftz: one MUFU instead of exp2f's range check + two scalings (results below 2^-126 flush to zero)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool SLIM>
+__device__ __forceinline__ float exp2_sel(float x) {
+    if constexpr (SLIM) return ex2_approx(x);
+    else return exp2f(x);
+}
+
+template <bool SLIM>
 __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, const uint32_t (&qb)[8][2], WarpState& st,
                                              int tbase, int kv_len, float sl2, int g, int t) {
     const uint8_t* sK = stage;
@@ -231,11 +244,11 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
         m_new[c] = fmaxf(st.m_run[c], mx);
         moved |= m_new[c] != st.m_run[c];
         m_safe[c] = m_new[c] == -INFINITY ? 0.f : m_new[c];
-        pv[c][0] = exp2f(sv[c][0] - m_safe[c]);
-        pv[c][1] = exp2f(sv[c][1] - m_safe[c]);
+        pv[c][0] = exp2_sel<SLIM>(sv[c][0] - m_safe[c]);
+        pv[c][1] = exp2_sel<SLIM>(sv[c][1] - m_safe[c]);
     }
     if (__any_sync(0xffffffffu, moved)) {  // some running max moved: rescale (rare after the first units)
-        const float c0 = exp2f(st.m_run[0] - m_safe[0]), c1 = exp2f(st.m_run[1] - m_safe[1]);
+        const float c0 = exp2_sel<SLIM>(st.m_run[0] - m_safe[0]), c1 = exp2_sel<SLIM>(st.m_run[1] - m_safe[1]);
         st.l_run[0] *= c0;
         st.l_run[1] *= c1;
 #pragma unroll
@@ -285,10 +298,15 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
     }
 }
 
-template <int G, int WARPS, bool TMA>  // G: q heads per CTA (rows of the MMA M dimension in use), 1..8
+// G: q heads per CTA (rows of the MMA M dimension in use), 1..8.  LOADER: 0 cp.async, 1 TMA, 2 TMA "slim" -- same
+// data path and arithmetic as 1 with fewer instructions per unit around it: the page table is walked incrementally
+// (no integer division per unit in the issuing lane) and exp2 is a bare ex2.approx.  The kernel's time follows the
+// SM clock (in-step 1837 MHz: 0.896 ms, alone 1965 MHz: 0.838 ms), i.e. it is issue-bound before it is HBM-bound.
+template <int G, int WARPS, int LOADER>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
                        DecodeTma tc) {
+    constexpr bool TMA = LOADER != 0, SLIM = LOADER == 2;
     extern __shared__ uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -352,6 +370,34 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         return p.cache_indices[(int64_t)b * p.max_pages + pos / p.page_size] + pos % p.page_size;
     };
 
+    // SLIM: position of the next unit to issue as (page-table entry, token offset inside the page), advanced by
+    // WARPS units per issue -- the divisions happen once here instead of once per unit
+    int walk_page = 0, walk_off = 0, adv_page = 0, adv_off = 0;
+    if constexpr (SLIM) {
+        const int pos0 = (u0 + warp) * UNIT;
+        if (p.cache_mode == 0) {
+            walk_off = pos0;            // slot = cache_indices[b] + position: one "page" of unbounded size
+            adv_off = WARPS * UNIT;
+        } else {
+            walk_page = pos0 / p.page_size;
+            walk_off = pos0 % p.page_size;
+            adv_page = (WARPS * UNIT) / p.page_size;
+            adv_off = (WARPS * UNIT) % p.page_size;
+        }
+    }
+    auto walk_slot0 = [&]() -> int64_t {  // first cache slot of the unit the walk points at
+        if (p.cache_mode == 0) return p.cache_indices[b] + walk_off;
+        return p.cache_indices[(int64_t)b * p.max_pages + walk_page] + walk_off;
+    };
+    auto walk_advance = [&]() {
+        walk_page += adv_page;
+        walk_off += adv_off;
+        if (p.cache_mode != 0 && walk_off >= p.page_size) {
+            walk_off -= p.page_size;
+            ++walk_page;
+        }
+    };
+
     // ---- loader: fill stage `st` of this warp's ring with unit u
     const int8_t* kbase = p.cache + hk * p.cs.head;
     const int8_t* vbase = kbase + p.cs.kv;
@@ -361,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         const uint32_t sK = wsm_u32 + st * STAGE, sV = sK + K_BYTES, sKS = sV + K_BYTES, sVS = sKS + S_BYTES;
         if constexpr (TMA) {
             if (lane == 0) {
-                const int s0 = (int)unit_slot0(u);
+                const int s0 = SLIM ? (int)walk_slot0() : (int)unit_slot0(u);
                 const uint32_t bar = wbar + 8u * st;
                 mbar_expect_tx(bar, STAGE);
                 if (tc.tok_dim == 1) {
@@ -418,6 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     for (int s = 0; s < NSTAGE - 1; ++s) {
         if (u_issue < u1) load_unit(u_issue, s);
         if constexpr (!TMA) cp_async_commit();
+        if constexpr (SLIM) walk_advance();
         u_issue += WARPS;
     }
     int stg = 0;
@@ -433,6 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
             const int st_next = (stg + NSTAGE - 1) % NSTAGE;
             if (u_issue < u1) load_unit(u_issue, st_next);
             if constexpr (!TMA) cp_async_commit();
+            if constexpr (SLIM) walk_advance();
             u_issue += WARPS;
         }
         uint8_t* stage = wsm + stg * STAGE;
@@ -449,7 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
                 __syncwarp();
             }
         }
-        process_unit(stage, qa, st, u * UNIT, kv_len, sl2, g, t);
+        process_unit<SLIM>(stage, qa, st, u * UNIT, kv_len, sl2, g, t);
         if (++stg == NSTAGE) { stg = 0; phase ^= 1; }
     }
     if constexpr (!TMA) cp_async_wait<0>();
@@ -662,7 +710,7 @@ DecodeTma make_tma_coords(const AttnArgs& a) {
     return c;
 }
 
-int g_attn_warps_override = -1, g_attn_tma_override = -1;
+int g_attn_warps_override = -1, g_attn_tma_override = -1, g_attn_slim = -1;
 std::once_flag g_attn_env_once;
 
 }  // namespace
@@ -694,9 +742,9 @@ int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token
     return B2LLM_OK;
 }
 
-template <int G, int WARPS, bool TMA>
+template <int G, int WARPS, int LOADER>
 static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc) {
-    auto kern = attn_decode_kernel<G, WARPS, TMA>;
+    auto kern = attn_decode_kernel<G, WARPS, LOADER>;
     constexpr int smem_bytes = WARPS * NSTAGE * STAGE + 1024 + 8 * WARPS * NSTAGE + 64 +
                                (WARPS * G * 130 * 4 > WARPS * NSTAGE * STAGE ? WARPS * G * 130 * 4 : 0);
     B2_ENSURE_DYN_SMEM(kern, smem_bytes);
@@ -714,15 +762,21 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
 }
 
 template <int G>
-static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc, int warps, bool tma) {
-    if (tma) {
-        if (warps == 1) return launch_decode<G, 1, true>(s, p, maps, tc);
-        if (warps == 2) return launch_decode<G, 2, true>(s, p, maps, tc);
-        return launch_decode<G, 4, true>(s, p, maps, tc);
+static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc, int warps, bool tma,
+                               bool slim) {
+    if (tma && slim) {
+        if (warps == 1) return launch_decode<G, 1, 2>(s, p, maps, tc);
+        if (warps == 2) return launch_decode<G, 2, 2>(s, p, maps, tc);
+        return launch_decode<G, 4, 2>(s, p, maps, tc);
     }
-    if (warps == 1) return launch_decode<G, 1, false>(s, p, maps, tc);
-    if (warps == 2) return launch_decode<G, 2, false>(s, p, maps, tc);
-    return launch_decode<G, 4, false>(s, p, maps, tc);
+    if (tma) {
+        if (warps == 1) return launch_decode<G, 1, 1>(s, p, maps, tc);
+        if (warps == 2) return launch_decode<G, 2, 1>(s, p, maps, tc);
+        return launch_decode<G, 4, 1>(s, p, maps, tc);
+    }
+    if (warps == 1) return launch_decode<G, 1, 0>(s, p, maps, tc);
+    if (warps == 2) return launch_decode<G, 2, 0>(s, p, maps, tc);
+    return launch_decode<G, 4, 0>(s, p, maps, tc);
 }
 
 int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
@@ -733,6 +787,7 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     std::call_once(g_attn_env_once, [] {
         if (const char* e = getenv("B2LLM_ATTN_WARPS")) g_attn_warps_override = atoi(e);
         if (const char* e = getenv("B2LLM_ATTN_TMA")) g_attn_tma_override = atoi(e);
+        if (const char* e = getenv("B2LLM_ATTN_SLIM")) g_attn_slim = atoi(e);
     });
     AttnParams p = make_params(a);
     const int gq = p.nq / p.nkv;
@@ -759,9 +814,14 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
         if (!make_kv_maps(a, &maps)) tma = false;
         else tc = make_tma_coords(a);
     }
-    if (G == 1) return dispatch_decode<1>(s, p, maps, tc, warps, tma);
-    if (G == 4) return dispatch_decode<4>(s, p, maps, tc, warps, tma);
-    return dispatch_decode<8>(s, p, maps, tc, warps, tma);
+    // slim loader (LOADER 2): on by default where it ran green on the device (run 17: attention op tests + engine
+    // generation tests with the loader in use; same box 0.882 vs 0.926 ms per launch, step +3.0 %): page_size 16 and the
+    // contiguous-index cache mode.  Other page sizes are covered by the CPU property test of the walk only, so they keep
+    // the dividing loader unless B2LLM_ATTN_SLIM=1; B2LLM_ATTN_SLIM=0 switches it off everywhere.
+    const bool slim = g_attn_slim < 0 ? (p.cache_mode == 0 || p.page_size == UNIT) : g_attn_slim != 0;
+    if (G == 1) return dispatch_decode<1>(s, p, maps, tc, warps, tma, slim);
+    if (G == 4) return dispatch_decode<4>(s, p, maps, tc, warps, tma, slim);
+    return dispatch_decode<8>(s, p, maps, tc, warps, tma, slim);
 }
 
 }  // namespace b2llm
