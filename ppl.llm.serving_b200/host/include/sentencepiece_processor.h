@@ -1,14 +1,25 @@
-// Stand-in for <sentencepiece_processor.h> (the OpenPPL sentencepiece fork is absent in this image and there
-// is no network).  OUT OF SCOPE component (SURVEY.md section 2.1 "Tokenizer"): the hot path is driven with
-// token-in/out requests that bypass the tokenizer (llm_generator.cc:790-801).  This stub lets the reference's
-// tokenizer headers compile and lets `offline_inference` run its four text prompts end to end with a
-// byte-level vocabulary: piece id = 3 + byte (0 <unk>, 1 <s>, 2 </s>), "Load" accepts any readable file.
-#ifndef B2LLM_SHIM_SENTENCEPIECE_PROCESSOR_H_
-#define B2LLM_SHIM_SENTENCEPIECE_PROCESSOR_H_
+// <sentencepiece_processor.h> for the reference's tokenizer front end (src/tokenizer/tokenizer_impl_sp.h:22-68):
+// a from-scratch SentencePiece *inference* implementation (host/src/sentencepiece.cc) -- the OpenPPL sentencepiece
+// fork the reference fetches (cmake/deps.cmake) is absent in this image and there is no network.
+//
+// What it reads and does ("tokenizer front end"):
+//   * `tokenizer.model` = a serialized sentencepiece ModelProto (pieces with score / type, TrainerSpec, NormalizerSpec),
+//     parsed with the same protobuf wire reader as the ONNX loader (host/src/onnx_wire.h);
+//   * BPE (LLaMA / LLaMA-2: model_type BPE, byte_fallback, identity normaliser, dummy prefix) and unigram models;
+//     normalisation = dummy prefix / extra-whitespace removal / whitespace escaping; a compiled character map
+//     (nmt_nfkc ...) is NOT interpreted -- Load() refuses such a model instead of tokenising differently;
+//   * Encode -> ids, Decode <- ids (byte pieces re-assembled to UTF-8, control pieces invisible, unknown -> " ⁇ ").
+// Parity is pinned against the official `sentencepiece` Python package on models trained in the test
+// (tests/test_tokenizer_cpu.py): identical ids and identical decoded text.
+//
+// A file whose first bytes are "b2llm-byte-level-tokenizer" selects a built-in byte-level vocabulary (id = 3 + byte;
+// 0 <unk>, 1 <s>, 2 </s>) -- a test aid for running `offline_inference` without a trained model.
+#ifndef B2LLM_SENTENCEPIECE_PROCESSOR_H_
+#define B2LLM_SENTENCEPIECE_PROCESSOR_H_
 
 #include "absl/strings/string_view.h"
 
-#include <fstream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -34,56 +45,36 @@ private:
 
 class SentencePieceProcessor final {
 public:
-    util::Status Load(absl::string_view filename) {
-        std::ifstream ifs{std::string(filename)};
-        if (!ifs.is_open()) {
-            return util::Status("cannot open tokenizer model [" + std::string(filename) + "]");
-        }
-        return util::Status();
-    }
-    util::Status Encode(absl::string_view input, std::vector<int>* ids) const {
-        ids->clear();
-        for (unsigned char c : input) {
-            ids->push_back(3 + (int)c);
-        }
-        return util::Status();
-    }
-    util::Status Decode(const int* ids, unsigned int len, std::string* out) const {
-        out->clear();
-        for (unsigned int i = 0; i < len; ++i) {
-            const int id = ids[i];
-            if (id >= 3 && id < 3 + 256) {
-                out->push_back((char)(id - 3));
-            } else if (id >= 3 + 256) { // outside the byte range: printable placeholder
-                *out += "<" + std::to_string(id) + ">";
-            }
-        }
-        return util::Status();
-    }
-    util::Status Decode(const std::vector<int>& ids, std::string* out) const {
-        return Decode(ids.data(), (unsigned int)ids.size(), out);
-    }
-    std::string IdToPiece(int id) const {
-        if (id >= 3 && id < 3 + 256) {
-            return std::string(1, (char)(id - 3));
-        }
-        return id == 1 ? "<s>" : id == 2 ? "</s>" : "<unk>";
-    }
-    int GetPieceSize() const {
-        return 32000;
-    }
-    int bos_id() const {
-        return 1;
-    }
-    int eos_id() const {
-        return 2;
-    }
-    int pad_id() const {
-        return -1;
-    }
-    int unk_id() const {
-        return 0;
-    }
+    SentencePieceProcessor();
+    ~SentencePieceProcessor();
+    SentencePieceProcessor(const SentencePieceProcessor&) = delete;
+    SentencePieceProcessor& operator=(const SentencePieceProcessor&) = delete;
+
+    util::Status Load(absl::string_view filename);
+    util::Status LoadFromSerializedProto(absl::string_view serialized);
+
+    util::Status Encode(absl::string_view input, std::vector<int>* ids) const;
+    util::Status Encode(absl::string_view input, std::vector<std::string>* pieces) const;
+    // (ids, len) form: the OpenPPL fork's overload the reference calls (tokenizer_impl_sp.h:53)
+    util::Status Decode(const int* ids, unsigned int len, std::string* out) const;
+    util::Status Decode(const std::vector<int>& ids, std::string* out) const;
+
+    int GetPieceSize() const;
+    int PieceToId(absl::string_view piece) const;
+    const std::string& IdToPiece(int id) const;
+    float GetScore(int id) const;
+    bool IsUnknown(int id) const;
+    bool IsControl(int id) const;
+    bool IsUnused(int id) const;
+    bool IsByte(int id) const;
+    int unk_id() const;
+    int bos_id() const;
+    int eos_id() const;
+    int pad_id() const;
+
+private:
+    struct Impl;
+    std::unique_ptr<Impl> impl_;
 };
 
 } // namespace sentencepiece

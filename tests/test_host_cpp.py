@@ -237,10 +237,12 @@ def test_reference_generator_more_requests_than_batch_slots(tmp_path):
 @needs_ref
 def test_reference_offline_inference_tool_runs(tmp_path):
     """tools/offline_inference.cc, unchanged: 4 text prompts, generation lengths 8..11, greedy.  The tokenizer
-    behind it is the byte-level stand-in (sentencepiece is absent here), so only the flow is asserted."""
+    runs this repo's sentencepiece implementation (host/src/sentencepiece.cc, parity-tested against the official package in
+    tests/test_tokenizer_cpu.py) on its built-in byte-level test vocabulary, so that every id a random-init model emits
+    decodes; only the flow is asserted."""
     desc = ModelDesc(512, 1024, 2, 4, 4, 32000, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=512)
     mdir = write_model_dir(tmp_path / "model", desc, seed=0xB200)
-    (tmp_path / "tokenizer.model").write_text("byte-level stand-in")
+    (tmp_path / "tokenizer.model").write_text("b2llm-byte-level-tokenizer\n")
     r = _run([OFFLINE, "--model-dir", mdir, "--model-param-path", mdir / "params.json", "--tokenizer-path",
               tmp_path / "tokenizer.model", "--quant-method", "online_i8i8", "--max-tokens-scale", "0.01",
               "--max-running-batch", "16", "--max-tokens-per-step", "512"], log="INFO")
