@@ -302,11 +302,14 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
 // data path and arithmetic as 1 with fewer instructions per unit around it: the page table is walked incrementally
 // (no integer division per unit in the issuing lane) and exp2 is a bare ex2.approx.  The kernel's time follows the
 // SM clock (in-step 1837 MHz: 0.896 ms, alone 1965 MHz: 0.838 ms), i.e. it is issue-bound before it is HBM-bound.
+// LOADER 3 (opt-in, B2LLM_ATTN_SLIM=2; NOT yet run on a device): slim + K and V of a unit in ONE 4-D TMA box
+// {row bytes, 16 tokens, 1 head, 2 (k, v)} and their scales in another -- 2 bulk loads per unit instead of 4
+// (cache layouts 2 and 3, where k / v is an outer dimension; the smem image is unchanged: K | V | K scales | V scales).
 template <int G, int WARPS, int LOADER>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
                        DecodeTma tc) {
-    constexpr bool TMA = LOADER != 0, SLIM = LOADER == 2;
+    constexpr bool TMA = LOADER != 0, SLIM = LOADER >= 2, MERGED = LOADER == 3;
     extern __shared__ uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -410,7 +413,15 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
                 const int s0 = SLIM ? (int)walk_slot0() : (int)unit_slot0(u);
                 const uint32_t bar = wbar + 8u * st;
                 mbar_expect_tx(bar, STAGE);
-                if (tc.tok_dim == 1) {
+                if constexpr (MERGED) {
+                    if (tc.tok_dim == 1) {
+                        tma_load_4d(sK, &map_kv, bar, 0, s0, hk, tc.k_fixed);
+                        tma_load_4d(sKS, &map_sc, bar, 0, s0, hk, tc.k_fixed);
+                    } else {
+                        tma_load_4d(sK, &map_kv, bar, 0, hk, s0, tc.k_fixed);
+                        tma_load_4d(sKS, &map_sc, bar, 0, hk, s0, tc.k_fixed);
+                    }
+                } else if (tc.tok_dim == 1) {
                     tma_load_3d(sK, &map_kv, bar, 0, tc.k_tok0 + s0, tc.k_fixed + hk);
                     tma_load_3d(sV, &map_kv, bar, 0, tc.v_tok0 + s0, tc.v_fixed + hk);
                     tma_load_3d(sKS, &map_sc, bar, 0, tc.k_tok0 + s0, tc.k_fixed + hk);
@@ -696,6 +707,55 @@ bool make_kv_maps(const AttnArgs& a, KvMaps* out) {
     return true;
 }
 
+// 4-D maps for LOADER 3: k / v as the outermost box dimension (layouts 2 and 3 only)
+//   layout 3 [L,2,H,T,D]: {D, T, H, L*2}   box {D,16,1,2}   coords (0, slot, h, l*2)
+//   layout 2 [L,2,T,H,D]: {D, H, T, L*2}   box {D,1,16,2}   coords (0, h, slot, l*2)
+std::map<std::tuple<const void*, const void*, int, int, int, int, uint64_t>, KvMaps> g_kvmap4_cache;
+
+bool make_kv_maps_merged(const AttnArgs& a, KvMaps* out) {
+    const b2llm_kv_geom& g = a.geom;
+    if (g.cache_layout != 2 && g.cache_layout != 3) return false;
+    auto key = std::make_tuple((const void*)a.kv_cache, (const void*)a.kv_scale, g.cache_layout, g.num_layers, g.num_kv_heads,
+                               g.head_dim, (uint64_t)g.max_tokens);
+    std::lock_guard<std::mutex> lk(g_kvmap_mutex);
+    auto it = g_kvmap4_cache.find(key);
+    if (it != g_kvmap4_cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    const uint64_t L = g.num_layers, H = g.num_kv_heads, T = g.max_tokens;
+    for (int which = 0; which < 2; ++which) {
+        const uint64_t rb = which == 0 ? 128 : 32;
+        uint64_t dims[4], strides[3];
+        uint32_t box[4];
+        dims[0] = rb;
+        dims[3] = L * 2;
+        box[0] = (uint32_t)rb;
+        box[3] = 2;
+        if (g.cache_layout == 3) {
+            dims[1] = T; dims[2] = H; box[1] = UNIT; box[2] = 1;
+        } else {
+            dims[1] = H; dims[2] = T; box[1] = 1; box[2] = UNIT;
+        }
+        strides[0] = rb;
+        strides[1] = rb * dims[1];
+        strides[2] = rb * dims[1] * dims[2];
+        if (!tma_encode_bytes(which == 0 ? &out->kv : &out->sc, which == 0 ? (const void*)a.kv_cache : (const void*)a.kv_scale,
+                              4, dims, strides, box, which == 0))
+            return false;
+    }
+    if (g_kvmap4_cache.size() > 64) g_kvmap4_cache.clear();
+    g_kvmap4_cache[key] = *out;
+    return true;
+}
+
+DecodeTma make_tma_coords_merged(const AttnArgs& a) {
+    DecodeTma c{};
+    c.tok_dim = a.geom.cache_layout == 3 ? 1 : 2;
+    c.k_fixed = a.layer * 2;  // the (layer, k/v) coordinate of K; V is the second element of the box
+    return c;
+}
+
 DecodeTma make_tma_coords(const AttnArgs& a) {
     const b2llm_kv_geom& g = a.geom;
     const int L = a.layer, H = g.num_kv_heads;
@@ -763,7 +823,12 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
 
 template <int G>
 static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc, int warps, bool tma,
-                               bool slim) {
+                               int slim) {
+    if (tma && slim == 2) {
+        if (warps == 1) return launch_decode<G, 1, 3>(s, p, maps, tc);
+        if (warps == 2) return launch_decode<G, 2, 3>(s, p, maps, tc);
+        return launch_decode<G, 4, 3>(s, p, maps, tc);
+    }
     if (tma && slim) {
         if (warps == 1) return launch_decode<G, 1, 2>(s, p, maps, tc);
         if (warps == 2) return launch_decode<G, 2, 2>(s, p, maps, tc);
@@ -818,7 +883,17 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     // generation tests with the loader in use; same box 0.882 vs 0.926 ms per launch, step +3.0 %): page_size 16 and the
     // contiguous-index cache mode.  Other page sizes are covered by the CPU property test of the walk only, so they keep
     // the dividing loader unless B2LLM_ATTN_SLIM=1; B2LLM_ATTN_SLIM=0 switches it off everywhere.
-    const bool slim = g_attn_slim < 0 ? (p.cache_mode == 0 || p.page_size == UNIT) : g_attn_slim != 0;
+    int slim = g_attn_slim < 0 ? (p.cache_mode == 0 || p.page_size == UNIT) : g_attn_slim;
+    if (a.loader >= 0) slim = a.loader;  // explicit choice of the caller (parity tests of every loader)
+    if (tma && slim == 2) {  // merged K + V loads: layouts 2 / 3 only, else the plain slim loader
+        KvMaps merged{};
+        if (make_kv_maps_merged(a, &merged)) {
+            maps = merged;
+            tc = make_tma_coords_merged(a);
+        } else {
+            slim = 1;
+        }
+    }
     if (G == 1) return dispatch_decode<1>(s, p, maps, tc, warps, tma, slim);
     if (G == 4) return dispatch_decode<4>(s, p, maps, tc, warps, tma, slim);
     return dispatch_decode<8>(s, p, maps, tc, warps, tma, slim);

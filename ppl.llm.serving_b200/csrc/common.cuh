@@ -202,6 +202,7 @@ struct AttnArgs {
     void* workspace;
     __half* out;           // [T, nq * D]
     int split_k = 1;       // ENGINE_CONF_DECODING_ATTN_SPLIT_K: 0 off, 1 heuristic, 2 always
+    int loader = -1;       // decode kernel's TMA loader: -1 auto (env / default), 0 dividing, 1 slim, 2 slim + merged K/V loads
 };
 int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* step, int num_heads,
                               const b2llm_kv_geom& geom, int layer, const float* cos_t, const float* sin_t,

@@ -911,6 +911,7 @@ extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const 
     aa.workspace = workspace;
     aa.out = (__half*)out_fp16;
     cudaStream_t s = (cudaStream_t)stream;
+    if (impl >= 3 && impl <= 5) aa.loader = impl == 3 ? 2 : (impl == 4 ? 0 : 1);
     if (impl == 1 || (impl == 0 && geom->head_dim != 128)) return launch_attention_simple(s, aa, 0, step->num_tokens);
     B2_REQUIRE(workspace, B2LLM_ERR_INVALID_VALUE, "attention: workspace required");
     int32_t rc = launch_attention_decode_mma(s, aa);

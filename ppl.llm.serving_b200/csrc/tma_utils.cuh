@@ -9,7 +9,7 @@ namespace b2llm {
 // host: cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dependency)
 bool tma_available();
 int device_num_sms();
-// byte tensor of rank 2 or 3; dims[0] is the contiguous dimension; strides[i] = byte stride of dim i + 1
+// byte tensor of rank 2 .. 5; dims[0] is the contiguous dimension; strides[i] = byte stride of dim i + 1
 bool tma_encode_bytes(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box, bool swizzle128);
 
@@ -44,6 +44,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map));

@@ -5,6 +5,7 @@ GEMM results after the fixed-order fp32 dequant, rope, KV bytes); for kernels wh
 order legitimately differs (row norms, softmax, fp16 GEMM) the tolerance is stated at the assert.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -404,6 +405,33 @@ def test_attention_long_ragged_batch(lib):
     rng = np.random.default_rng(0)
     lens = [int(x) for x in rng.integers(1, 400, 48)]
     _attention_case(lib, desc, [1] * 48, lens, 48, 2, T_cache=48 * 416, seed=5)
+
+
+@pytest.mark.parametrize("impl", [4, 5])  # 4: dividing loader (default until run 17), 5: slim loader (default since)
+@pytest.mark.parametrize("layout,mode", [(3, 1), (1, 0)])
+def test_attention_decode_both_validated_loaders(lib, impl, layout, mode):
+    """the decode kernel's two device-validated TMA loaders, selected explicitly (b2llm_op_attention impl 4 / 5), on
+    the shapes of test_attention_decode_mha / _gqa_and_splits / _long_ragged_batch"""
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4), [1] * 5, [0, 15, 16, 100, 333], 5, impl, seed=layout)
+    _attention_case(lib, _mk_desc(layout, mode, nq=8, nkv=1), [1, 1], [1500, 700], 2, impl, T_cache=4096, seed=3)
+    rng = np.random.default_rng(0)
+    lens = [int(x) for x in rng.integers(1, 400, 48)]
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4), [1] * 48, lens, 48, impl, T_cache=48 * 416, seed=5)
+
+
+@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
+                    reason="kernels that have not run on a device yet (set B2LLM_TEST_EXPERIMENTAL=1): kept out of the default "
+                           "suite because a faulting kernel poisons the CUDA context for every later test")
+@pytest.mark.parametrize("layout,mode,page", [(3, 1, 16), (2, 0, 16), (3, 0, 16), (2, 1, 64), (3, 1, 128), (1, 0, 16)])
+def test_attention_decode_merged_loader_experimental(lib, layout, mode, page):
+    """impl 3: slim loader + K and V of a unit in one 4-D TMA box (LOADER 3, layouts 2 / 3; layout 1 falls back to slim).
+    Also the only GPU coverage of the incremental page walk at page sizes other than 16."""
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 5, [0, 15, 16, 100, 333], 5, 3, seed=layout)
+    _attention_case(lib, _mk_desc(layout, mode, nq=8, nkv=1, page=page), [1, 1], [1500, 700], 2, 3, T_cache=4096, seed=3)
+    rng = np.random.default_rng(0)
+    lens = [int(x) for x in rng.integers(1, 400, 48)]
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 48, lens, 48, 3, T_cache=48 * 512, seed=5)
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 5, [0, 15, 16, 100, 333], 5, 5, seed=layout)
 
 
 # ------------------------------------------------------------------ sampler / penalty
