@@ -362,3 +362,23 @@ def test_reference_generator_prefix_cache_hit(tmp_path):
     want0, want1 = decode(p0, l0, pt0), decode(p1, l1, pt1)
     assert got[0] == want0
     assert got[1] == want1
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
+                    reason="not yet run on a device (set B2LLM_TEST_EXPERIMENTAL=1); compiled and linked by `make ref`")
+def test_reference_prefix_cache_benchmark_tool_runs(tmp_path):
+    """tools/benchmark_prefix_cache_offline.cc, unchanged: 3 warm-ups, one ~1700-character prompt
+    generated twice with --enable-prefix-cache; the second pass must hit the cache and report a smaller TTFT"""
+    tool = REFDIR / "benchmark_prefix_cache_offline"
+    desc = ModelDesc(512, 1024, 2, 4, 4, 32000, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=4096)
+    mdir = write_model_dir(tmp_path / "model", desc, seed=0xB200)
+    (tmp_path / "tokenizer.model").write_text("b2llm-byte-level-tokenizer\n")
+    r = _run([tool, "--model-dir", mdir, "--model-param-path", mdir / "params.json", "--tokenizer-path",
+              tmp_path / "tokenizer.model", "--quant-method", "online_i8i8", "--max-tokens-scale", "0.01",
+              "--max-running-batch", "16", "--max-tokens-per-step", "4096", "--enable-prefix-cache", "1"], log="INFO")
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = dict(l.split(": ") for l in r.stdout.strip().splitlines() if ": " in l)
+    assert "first ttft" in out and "prefix ttft" in out, r.stdout
+    assert "Cache Hit" in r.stderr
