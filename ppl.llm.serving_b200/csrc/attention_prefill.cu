@@ -282,4 +282,16 @@ int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a) {
     return B2LLM_OK;
 }
 
+int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, bool force_tc) {
+    static const bool env_tc = [] {
+        const char* e = getenv("B2LLM_PREFILL_IMPL");
+        return e != nullptr && e[0] == 't';
+    }();
+    if (force_tc || env_tc) {
+        const int32_t rc = launch_attention_prefill_tc(s, a);
+        if (rc != B2LLM_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_attention_prefill_mma(s, a);
+}
+
 }  // namespace b2llm

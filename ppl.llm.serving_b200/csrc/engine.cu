@@ -723,7 +723,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
                 if ((rc = launch_attention_simple(s, aa, 0, T))) return rc;
             } else {
                 if ((rc = launch_attention_decode_mma(s, aa))) return rc;
-                if (decode_tokens < T && (rc = launch_attention_prefill_mma(s, aa))) return rc;
+                if (decode_tokens < T && (rc = launch_attention_prefill(s, aa))) return rc;
             }
         }
         if (i8) {
@@ -912,12 +912,13 @@ extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const 
     aa.out = (__half*)out_fp16;
     cudaStream_t s = (cudaStream_t)stream;
     if (impl >= 3 && impl <= 5) aa.loader = impl == 3 ? 2 : (impl == 4 ? 0 : 1);
+    const bool prefill_tc = impl == 6;  // experimental tcgen05 prefill kernel
     if (impl == 1 || (impl == 0 && geom->head_dim != 128)) return launch_attention_simple(s, aa, 0, step->num_tokens);
     B2_REQUIRE(workspace, B2LLM_ERR_INVALID_VALUE, "attention: workspace required");
     int32_t rc = launch_attention_decode_mma(s, aa);
     if (rc) return rc;
     if (step->decoding_batches >= step->batch) return B2LLM_OK;
-    return launch_attention_prefill_mma(s, aa);
+    return launch_attention_prefill(s, aa, prefill_tc);
 }
 
 extern "C" int32_t b2llm_op_synth_fp16(void* stream, uint64_t seed, uint64_t tensor_id, uint64_t num_elements, float std,

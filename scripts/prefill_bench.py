@@ -20,6 +20,7 @@ from ppl_llm_serving_b200.engine import _ptr  # noqa: E402
 
 lib = capi.load_library()
 SEQS, LEN, H, D = int(os.environ.get("SEQS", 8)), int(os.environ.get("LEN", 4096)), 32, 128
+IMPL = int(os.environ.get("IMPL", 2))  # 2: mma.sync prefill kernel, 6: tcgen05 / TMEM kernel (experimental)
 T = SEQS * LEN
 geom = capi.KvGeomC()
 geom.num_layers, geom.num_kv_heads, geom.head_dim, geom.quant_group = 1, H, D, 8
@@ -42,7 +43,7 @@ sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def run():
-    rc = lib.b2llm_op_attention(sp, _ptr(qkv), C.byref(st), H, C.byref(geom), 0, _ptr(cache), _ptr(scale), _ptr(ws), _ptr(out), 2)
+    rc = lib.b2llm_op_attention(sp, _ptr(qkv), C.byref(st), H, C.byref(geom), 0, _ptr(cache), _ptr(scale), _ptr(ws), _ptr(out), IMPL)
     assert rc == 0, lib.b2llm_last_error()
 
 

@@ -313,7 +313,7 @@ def test_rope_kv_append_bit_exact(lib, layout, mode):
 
 
 # ------------------------------------------------------------------ attention
-def _attention_case(lib, desc, seqlens, start_pos, decoding, impl, T_cache=2048, seed=0):
+def _attention_case(lib, desc, seqlens, start_pos, decoding, impl, T_cache=2048, seed=0, cache_prefill=1):
     rng = np.random.default_rng(seed)
     step = _ragged_step(desc, rng, seqlens, start_pos, decoding, T_cache)
     D, nq, nkv = desc.head_dim, desc.num_heads, desc.num_kv_heads
@@ -351,7 +351,7 @@ def _attention_case(lib, desc, seqlens, start_pos, decoding, impl, T_cache=2048,
     c_np, s_np = cache.export()
     keep = []
     sc = make_step_c(step, keep)
-    sc.cache_prefill = 1
+    sc.cache_prefill = cache_prefill
     geom = make_geom(desc, T_cache)
     out = torch.zeros((T, nq * D), dtype=torch.float16, device="cuda")
     ws = torch.empty(lib.b2llm_attention_workspace_size(step.batch, nq, D), dtype=torch.uint8, device="cuda")
@@ -432,6 +432,20 @@ def test_attention_decode_merged_loader_experimental(lib, layout, mode, page):
     lens = [int(x) for x in rng.integers(1, 400, 48)]
     _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 48, lens, 48, 3, T_cache=48 * 512, seed=5)
     _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 5, [0, 15, 16, 100, 333], 5, 5, seed=layout)
+
+
+@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
+                    reason="kernels that have not run on a device yet (set B2LLM_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("nq,nkv", [(4, 4), (8, 2)])
+def test_attention_prefill_tcgen05_experimental(lib, nq, nkv):
+    """impl 6: the tcgen05 / TMEM prefill kernel (attention_prefill_tc.cu) on fresh prompts whose lengths straddle the
+    128-query tiles and 128-key blocks, alone and behind decode sequences; steps with cached prefixes must fall back to
+    the mma.sync kernel and still be right"""
+    desc = _mk_desc(3, 1, nq=nq, nkv=nkv)
+    for lens in ([1], [17], [127], [128], [129], [300, 64, 513], [700]):
+        _attention_case(lib, desc, lens, [0] * len(lens), 0, 6, T_cache=4096, seed=31 + len(lens), cache_prefill=0)
+    _attention_case(lib, desc, [1, 1, 200, 130], [77, 5, 0, 0], 2, 6, T_cache=4096, seed=41, cache_prefill=0)
+    _attention_case(lib, desc, [1, 200, 65], [77, 0, 48], 1, 6, T_cache=4096, seed=42)  # cached prefix -> fallback
 
 
 # ------------------------------------------------------------------ sampler / penalty
