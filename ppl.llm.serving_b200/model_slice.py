@@ -5,8 +5,10 @@
     <dir>/weights.fp16                      optional fp16 blob (full tensors; every rank slices its part)
 
 The reference addresses the model only by that path and by tensor index (llm_engine.h:124-138); what is inside
-``model.onnx`` is private to the runtime behind ``ppl::nn::onnx::RuntimeBuilder``.  ppl.pmx ONNX exports are
-not read yet; synthetic (seeded) weights or an fp16 blob are.  See INTEGRATION.md section 4.
+``model.onnx`` is private to the runtime behind ``ppl::nn::onnx::RuntimeBuilder``, which reads two kinds of file here:
+a real ppl.pmx ONNX export (host/src/{onnx_model,pmx_llama}.cc; written for tests by ``pmx_onnx_writer.py``) and this
+text descriptor for synthetic (seeded) weights or an fp16 blob -- what bench.py, the steady-state probe and most tests
+use, because it needs no multi-GB files.  See INTEGRATION.md section 4.
 """
 from __future__ import annotations
 
