@@ -207,7 +207,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # no device_id: the NCCL communicator is created lazily at the first collective (the barrier before the timed
+        # region), i.e. AFTER the KV budget has been taken from the free memory -- with eager creation NCCL's buffers eat
+        # the 0.7 GB of slack that decides between kv_len 512 and 496, and the N > 1 runs would time a different workload
+        dist.init_process_group("nccl")
 
     cfg = ModelConfig(**LLAMA2_7B, page_size=PAGE, max_position=4096)
     cfg.num_layers = args.layers
@@ -253,7 +256,7 @@ def main():
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
     stream = res.stream
