@@ -295,3 +295,33 @@ def test_runtime_builder_load_model_recognises_both_file_kinds(tmp_path):
     assert good.returncode == 0 and good.stdout.count("success") == 2, good.stdout + good.stderr
     bad = subprocess.run([str(exe), str(tmp_path / "junk.onnx")], capture_output=True, text=True, timeout=60, env=env)
     assert bad.returncode == 1 and "not an ONNX" in bad.stderr, bad.stdout + bad.stderr
+
+
+def test_parsers_survive_damaged_files(tmp_path):
+    """the ONNX model-slice loader and the sentencepiece model loader under AddressSanitizer + UBSan with truncated /
+    bit-flipped / length-bombed copies of valid files (host/tests/fuzz_loaders.cc): refusing is fine, crashing is not"""
+    import os
+    import subprocess
+    host = ROOT / "ppl.llm.serving_b200" / "host"
+    b = subprocess.run(["make", "-C", str(host), "build/fuzz_loaders"], capture_output=True, text=True, timeout=600)
+    if b.returncode != 0:
+        pytest.skip("sanitizer build not available: " + b.stderr[-300:])
+    desc = small_desc()
+    W.write_pmx_export(tmp_path / "inline", desc, SynthWeights(desc, 1))
+    W.write_pmx_export(tmp_path / "ext", desc, SynthWeights(desc, 1), external_data=True, fused_qkv=False, syntax="proto2")
+    seeds = [tmp_path / "inline/model_slice_0/model.onnx", tmp_path / "ext/model_slice_0/model.onnx"]
+    try:
+        import sentencepiece as spm
+        words = "the quick brown fox jumps over lazy dog hello world 北京 café".split()
+        rng = np.random.default_rng(0)
+        (tmp_path / "c.txt").write_text("\n".join(" ".join(rng.choice(words, 8)) for _ in range(2000)))
+        for mt in ("bpe", "unigram"):
+            spm.SentencePieceTrainer.train(input=str(tmp_path / "c.txt"), model_prefix=str(tmp_path / mt), vocab_size=300,
+                                           model_type=mt, byte_fallback=True, normalization_rule_name="identity",
+                                           minloglevel=2, hard_vocab_limit=False, num_threads=1)
+            seeds.append(tmp_path / f"{mt}.model")
+    except ImportError:
+        pass
+    r = subprocess.run([str(host / "build" / "fuzz_loaders"), "1200", "7"] + [str(s) for s in seeds], capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", PPL_LOG_LEVEL="ERROR"))
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
