@@ -24,8 +24,10 @@
 // S_j; the O update of block j is deferred until after P_{j+1} so that PV_j's latency is hidden as well.
 //
 // Numeric contract: oracle/llama_ref.py _attend (fp16 Q/K/V, fp32 scores and sums, P rounded to fp16 for the PV
-// product -- the mma.sync kernel carries P as hi + lo halves; should the e2e logits tolerance need it, PV can be
-// issued twice the same way).
+// product -- the mma.sync kernel carries P as hi + lo halves).  A numpy emulation of exactly this block schedule on
+// N(0,1) inputs puts the maximum error at 2.1e-4 .. 3.5e-4 of the output scale for prompt lengths 300 .. 4096 with
+// fp16 P and at 2.0e-4 .. 2.8e-4 with hi + lo: the final fp16 rounding of O dominates, so one PV product suffices for
+// the 2e-3 op tolerance (tests/test_ops_gpu.py) -- to be confirmed against the e2e logits tolerance on the device.
 #include <map>
 #include <mutex>
 #include <tuple>
