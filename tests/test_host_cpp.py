@@ -382,3 +382,30 @@ def test_reference_prefix_cache_benchmark_tool_runs(tmp_path):
     out = dict(l.split(": ") for l in r.stdout.strip().splitlines() if ": " in l)
     assert "first ttft" in out and "prefix ttft" in out, r.stdout
     assert "Cache Hit" in r.stderr
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
+                    reason="not yet run on a device (set B2LLM_TEST_EXPERIMENTAL=1)")
+def test_reference_offline_inference_with_trained_sentencepiece_model(tmp_path):
+    """offline_inference end to end with a REAL sentencepiece model (LLaMA-style BPE with byte fallback, trained here) and a
+    model whose vocabulary is the tokenizer's: prompts are tokenised by host/src/sentencepiece.cc, every generated id
+    decodes, answers are non-empty text"""
+    spm = pytest.importorskip("sentencepiece")
+    words = ("I believe the meaning of life is Simply put theory relativity states that Building a website can be done in "
+             "simple steps tweet sentiment hello world").split()
+    rng = np.random.default_rng(0)
+    (tmp_path / "c.txt").write_text("\n".join(" ".join(rng.choice(words, 9)) for _ in range(3000)))
+    spm.SentencePieceTrainer.train(input=str(tmp_path / "c.txt"), model_prefix=str(tmp_path / "tok"), vocab_size=512,
+                                   model_type="bpe", byte_fallback=True, normalization_rule_name="identity",
+                                   remove_extra_whitespaces=False, minloglevel=2, hard_vocab_limit=False, num_threads=1)
+    vocab = spm.SentencePieceProcessor(model_file=str(tmp_path / "tok.model")).get_piece_size()
+    desc = ModelDesc(512, 1024, 2, 4, 4, vocab, cache_layout=3, cache_mode=1, page_size=16, quant_method=1, max_position=512)
+    mdir = write_model_dir(tmp_path / "model", desc, seed=0xB200)
+    r = _run([OFFLINE, "--model-dir", mdir, "--model-param-path", mdir / "params.json", "--tokenizer-path",
+              tmp_path / "tok.model", "--quant-method", "online_i8i8", "--max-tokens-scale", "0.01",
+              "--max-running-batch", "16", "--max-tokens-per-step", "512"], log="INFO")
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stderr.count("Prompt: ") == 4 and r.stderr.count("Answer:") == 4
+    assert "Invalid id" not in r.stderr
