@@ -413,6 +413,8 @@ def test_attention_decode_both_validated_loaders(lib, impl, layout, mode):
     """the decode kernel's two device-validated TMA loaders, selected explicitly (b2llm_op_attention impl 4 / 5), on
     the shapes of test_attention_decode_mha / _gqa_and_splits / _long_ragged_batch"""
     _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4), [1] * 5, [0, 15, 16, 100, 333], 5, impl, seed=layout)
+    if (layout, mode) != (3, 1):
+        return  # the GQA / split / ragged shapes below ran on the device with layout 3 + paging only (runs 13 and 17)
     _attention_case(lib, _mk_desc(layout, mode, nq=8, nkv=1), [1, 1], [1500, 700], 2, impl, T_cache=4096, seed=3)
     rng = np.random.default_rng(0)
     lens = [int(x) for x in rng.integers(1, 400, 48)]
