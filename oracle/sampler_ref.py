@@ -67,12 +67,21 @@ def sample_topk_topp(logits, temperatures, top_p, rand, vocab, top_k, default_to
 
 
 def apply_penalty(logits, temperatures, repetition, presence, frequency, batch_slots, token_inputs,
-                  seqstarts, start_pos, vocab, count_map):
-    """in-place on ``logits`` [B, >=vocab] and ``count_map`` uint16 [slots, vocab]."""
+                  seqstarts, start_pos, vocab, count_map, next_pos=None):
+    """in-place on ``logits`` [B, >=vocab] and ``count_map`` uint16 [slots, vocab].
+
+    A slot's counts are cleared on the first step of a request: ``start_pos == 0``, or -- with ``next_pos`` (a dict
+    slot -> expected next position, kept by the caller across steps) -- whenever the step does not continue the slot's
+    previous one.  The second rule is what catches a request admitted on a prefix-cache hit, which enters at
+    ``start_pos = cache_hit_count`` (llm_generator.cc:229-242) into a slot another request used before."""
     B = len(start_pos)
     for b in range(B):
         slot = int(batch_slots[b])
-        if int(start_pos[b]) == 0:
+        reset = int(start_pos[b]) == 0
+        if next_pos is not None:
+            reset = reset or next_pos.get(slot, -1) != int(start_pos[b])
+            next_pos[slot] = int(start_pos[b]) + int(seqstarts[b + 1]) - int(seqstarts[b])
+        if reset:
             count_map[slot, :] = 0
         for t in token_inputs[int(seqstarts[b]): int(seqstarts[b + 1])]:
             if count_map[slot, int(t)] < 65535:

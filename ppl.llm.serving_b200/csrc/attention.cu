@@ -302,7 +302,7 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
 // data path and arithmetic as 1 with fewer instructions per unit around it: the page table is walked incrementally
 // (no integer division per unit in the issuing lane) and exp2 is a bare ex2.approx.  The kernel's time follows the
 // SM clock (in-step 1837 MHz: 0.896 ms, alone 1965 MHz: 0.838 ms), i.e. it is issue-bound before it is HBM-bound.
-// LOADER 3 (opt-in, B2LLM_ATTN_SLIM=2; NOT yet run on a device): slim + K and V of a unit in ONE 4-D TMA box
+// LOADER 3 (default for cache layouts 2 / 3 since round 2 run 1): slim + K and V of a unit in ONE 4-D TMA box
 // {row bytes, 16 tokens, 1 head, 2 (k, v)} and their scales in another -- 2 bulk loads per unit instead of 4
 // (cache layouts 2 and 3, where k / v is an outer dimension; the smem image is unchanged: K | V | K scales | V scales).
 template <int G, int WARPS, int LOADER>
@@ -879,11 +879,11 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
         if (!make_kv_maps(a, &maps)) tma = false;
         else tc = make_tma_coords(a);
     }
-    // slim loader (LOADER 2): on by default where it ran green on the device (run 17: attention op tests + engine
-    // generation tests with the loader in use; same box 0.882 vs 0.926 ms per launch, step +3.0 %): page_size 16 and the
-    // contiguous-index cache mode.  Other page sizes are covered by the CPU property test of the walk only, so they keep
-    // the dividing loader unless B2LLM_ATTN_SLIM=1; B2LLM_ATTN_SLIM=0 switches it off everywhere.
-    int slim = g_attn_slim < 0 ? (p.cache_mode == 0 || p.page_size == UNIT) : g_attn_slim;
+    // loader defaults = what ran green on the device: the slim loader (run 17 of round 1) and, since round 2 run 1
+    // (profiles/r2_bringup_run1.txt: all layouts x paged / indexed x page 16 / 64 / 128; in-step 0.849 vs 0.883 ms per
+    // launch), the merged K + V loads (LOADER 3) wherever the layout allows them (2 and 3; others fall back to slim).
+    // B2LLM_ATTN_SLIM = 0 dividing loader, 1 slim, 2 slim + merged loads.
+    int slim = g_attn_slim < 0 ? 2 : g_attn_slim;
     if (a.loader >= 0) slim = a.loader;  // explicit choice of the caller (parity tests of every loader)
     if (tma && slim == 2) {  // merged K + V loads: layouts 2 / 3 only, else the plain slim loader
         KvMaps merged{};

@@ -181,6 +181,7 @@ int32_t launch_embedding(cudaStream_t s, const int64_t* ids, const __half* table
                          __half* out);
 int32_t launch_gather_rows(cudaStream_t s, const __half* x, const int64_t* seq_starts, int64_t batch, int hidden,
                            __half* out);
+int32_t launch_interleave_blocks(cudaStream_t s, const float* src, int parts, int64_t rows, int cols, float* dst);
 
 int32_t launch_gemm_mma(cudaStream_t s, bool is_i8, const void* a, const float* a_scale, const void* w,
                         const float* w_scale, int64_t M, int N, int K, int epilogue, void* out, int64_t ldc);

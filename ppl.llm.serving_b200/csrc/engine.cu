@@ -26,16 +26,19 @@ namespace {
 
 // ---- NCCL through dlopen: no link-time dependency; the process' already-loaded libnccl is reused
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 nccl_allreduce_fn g_nccl_allreduce = nullptr;
+nccl_allgather_fn g_nccl_allgather = nullptr;
 std::once_flag g_nccl_once;
 void load_nccl() {
     std::call_once(g_nccl_once, [] {
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (h) g_nccl_allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+        if (h) g_nccl_allgather = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
     });
 }
-constexpr int kNcclFloat16 = 6, kNcclSum = 0;
+constexpr int kNcclFloat16 = 6, kNcclFloat32 = 7, kNcclSum = 0;
 
 struct DevBuf {
     void* p = nullptr;
@@ -92,9 +95,16 @@ struct b2llm_engine {
     DevBuf rope_cos, rope_sin;
     // activations
     DevBuf x, a8, a_s, qkv, attn, act, b8, b_s, tmp, y16, xl, yl, logits, attn_ws, w16_scratch;
+    // tp > 1: the lm head is vocab-parallel -- this rank holds rows [rank * head_rows, (rank + 1) * head_rows) of
+    // output.weight, computes its column block of the logits and the blocks are all-gathered (SURVEY 8(e);
+    // the reference reads the gathered logits on rank 0, llm_engine.cc:200)
+    bool head_split = false;
+    int head_rows = 0;
+    DevBuf logits_part, logits_gather;
     // staged inputs
     DevBuf in_tokens, in_seq_starts, in_kv_starts, in_start_pos, in_cache_idx;
     b2llm_step staged{};
+    bool page_table_staged = false;  // cache_mode 1: a page table uploaded by set_inputs is still on the device
     void* kv_cache = nullptr;
     void* kv_scale = nullptr;
     int64_t last_launches = 0;
@@ -196,6 +206,7 @@ int32_t allreduce_half(b2llm_engine* e, __half* buf, size_t count) {
     load_nccl();
     B2_REQUIRE(g_nccl_allreduce != nullptr, B2LLM_ERR_UNSUPPORTED, "tensor parallel: libnccl.so.2 not loadable");
     B2_REQUIRE(e->comm != nullptr, B2LLM_ERR_INVALID_VALUE, "tensor parallel: no NCCL communicator given");
+    Span span(e, 3);
     const int r = g_nccl_allreduce(buf, buf, count, kNcclFloat16, kNcclSum, e->comm, e->stream);
     B2_REQUIRE(r == 0, B2LLM_ERR_DEVICE, "ncclAllReduce failed with code " + std::to_string(r));
     return B2LLM_OK;
@@ -275,6 +286,14 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     e->geom.cache_layout = d.cache_layout;
     e->geom.cache_mode = d.cache_mode;
     e->geom.page_size = d.page_size;
+    e->head_rows = d.vocab_size;
+    if (tp > 1 && d.vocab_size % tp == 0 && (d.vocab_size / tp) % 32 == 0) {
+        const char* hs = getenv("B2LLM_TP_HEAD");  // "whole": every rank keeps (and multiplies by) the whole lm head
+        if (!(hs && hs[0] == 'w')) {
+            e->head_split = true;
+            e->head_rows = d.vocab_size / tp;
+        }
+    }
     if (const char* s = getenv("B2LLM_ATTN_IMPL")) e->attn_impl = atoi(s);
     if (const char* s = getenv("B2LLM_GEMM_IMPL")) e->gemm_impl = atoi(s);
 
@@ -297,7 +316,7 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     }
     chk(e->embedding.ensure((size_t)d.vocab_size * h * 2));
     chk(e->final_norm.ensure((size_t)h * 2));
-    chk(e->lm_head.ensure((size_t)d.vocab_size * h * 2));
+    chk(e->lm_head.ensure((size_t)e->head_rows * h * 2));
     const size_t half = e->D / 2;
     chk(e->rope_cos.ensure((size_t)d.max_position * half * 4));
     chk(e->rope_sin.ensure((size_t)d.max_position * half * 4));
@@ -329,7 +348,12 @@ extern "C" int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int
     const b2llm_model_desc& d = e->d;
     const bool i8 = d.quant_method == B2LLM_QUANT_ONLINE_I8I8;
     const int h = d.hidden_dim;
-    const size_t T = (size_t)std::max<int64_t>(max_tokens, e->cap_tokens), B = (size_t)std::max<int64_t>(max_batch, e->cap_batch);
+    // growth is geometric (a ramp of prefill sizes must not reallocate every step) and drops the contents: inputs staged
+    // by set_inputs are gone, so set_inputs has to follow (b2llm_engine_run refuses to run on stale staging)
+    auto grow = [](int64_t want, int64_t cap) { return (size_t)(want <= cap ? cap : std::max<int64_t>(want, cap + cap / 2)); };
+    const size_t T = grow(max_tokens, e->cap_tokens), B = grow(max_batch, e->cap_batch);
+    e->staged = b2llm_step{};
+    e->page_table_staged = false;
     int32_t rc = B2LLM_OK;
     auto chk = [&](int32_t r) { if (rc == B2LLM_OK) rc = r; };
     const size_t amax_cols = (size_t)(h > e->nq * e->D ? h : e->nq * e->D);
@@ -346,6 +370,10 @@ extern "C" int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int
     chk(e->xl.ensure(B * h * 2));
     chk(e->yl.ensure(B * h * 2));
     chk(e->logits.ensure(B * (size_t)d.vocab_size * 4));
+    if (e->head_split) {
+        chk(e->logits_part.ensure(B * (size_t)e->head_rows * 4));
+        chk(e->logits_gather.ensure(B * (size_t)d.vocab_size * 4));
+    }
     chk(e->attn_ws.ensure((size_t)attention_workspace_bytes(B, e->nq, e->D)));
     chk(e->in_tokens.ensure(T * 8));
     chk(e->in_seq_starts.ensure((B + 1) * 8));
@@ -391,7 +419,7 @@ extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : {&e->embedding, &e->final_norm, &e->lm_head, &e->rope_cos, &e->rope_sin, &e->x, &e->a8, &e->a_s,
                       &e->qkv, &e->attn, &e->act, &e->b8, &e->b_s, &e->tmp, &e->y16, &e->xl, &e->yl, &e->logits,
-                      &e->attn_ws, &e->w16_scratch, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
+                      &e->attn_ws, &e->w16_scratch, &e->logits_part, &e->logits_gather, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
                       &e->in_cache_idx})
         b->release();
     delete e;
@@ -463,10 +491,23 @@ int32_t load_weight_impl(b2llm_engine* e, int32_t kind, int32_t layer, const voi
         }
         return true;
     };
-    if (kind == B2LLM_W_EMBEDDING || kind == B2LLM_W_LM_HEAD) {
+    if (kind == B2LLM_W_EMBEDDING) {
         if (!expect((uint64_t)d.vocab_size * h)) return B2LLM_ERR_INVALID_VALUE;
-        DevBuf& dst = kind == B2LLM_W_EMBEDDING ? e->embedding : e->lm_head;
-        B2_CHECK_CUDA(cudaMemcpyAsync(dst.p, src, num_elements * 2, cudaMemcpyHostToDevice, e->stream));
+        B2_CHECK_CUDA(cudaMemcpyAsync(e->embedding.p, src, num_elements * 2, cudaMemcpyHostToDevice, e->stream));
+        B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        return B2LLM_OK;
+    }
+    if (kind == B2LLM_W_LM_HEAD) {
+        // vocab-parallel head (tp > 1): the whole [vocab, h] tensor (this rank's row window is cut out) or, from
+        // load_weight_shard, the rank's own [vocab / tp, h] slice exactly as model_slice_<rank> stores it
+        const uint64_t whole = (uint64_t)d.vocab_size * h, part = (uint64_t)e->head_rows * h;
+        if (sharded && e->head_split && num_elements == part) {
+            B2_CHECK_CUDA(cudaMemcpyAsync(e->lm_head.p, src, part * 2, cudaMemcpyHostToDevice, e->stream));
+        } else {
+            if (!expect(whole)) return B2LLM_ERR_INVALID_VALUE;
+            const __half* win = src + (e->head_split ? (uint64_t)e->rank * part : 0);
+            B2_CHECK_CUDA(cudaMemcpyAsync(e->lm_head.p, win, part * 2, cudaMemcpyHostToDevice, e->stream));
+        }
         B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
         return B2LLM_OK;
     }
@@ -559,7 +600,8 @@ extern "C" int32_t b2llm_engine_random_init(b2llm_engine* e, uint64_t seed) {
     const float STD_EMBED = 1.0f, STD_W = 0.02f, STD_NORM = 0.02f;
     int32_t rc = launch_synth_fp16(s, seed, 1, (uint64_t)d.vocab_size * h, STD_EMBED, 0.f, e->embedding.as<__half>());
     if (!rc) rc = launch_synth_fp16(s, seed, 2, (uint64_t)h, STD_NORM, 1.f, e->final_norm.as<__half>());
-    if (!rc) rc = launch_synth_fp16(s, seed, 3, (uint64_t)d.vocab_size * h, STD_W, 0.f, e->lm_head.as<__half>());
+    if (!rc) rc = launch_synth_fp16_2d(s, seed, 3, e->head_rows, h, e->head_split ? (int64_t)e->rank * e->head_rows : 0, 0, h, STD_W,
+                                       0.f, e->lm_head.as<__half>());
     if (rc) return rc;
     DevBuf stage, stage2, stage3;
     const size_t big = (size_t)(2 * e->inter > e->nqkv ? 2 * e->inter : e->nqkv) * h;
@@ -632,6 +674,11 @@ extern "C" int32_t b2llm_engine_set_inputs(b2llm_engine* e, const int64_t* token
         }
         B2_CHECK_CUDA(cudaMemcpyAsync(e->in_cache_idx.p, cache_indices_or_page_list, bytes, cudaMemcpyHostToDevice, s));
         e->staged.max_pages = max_pages;
+        e->page_table_staged = true;
+    } else {
+        B2_REQUIRE(e->page_table_staged, B2LLM_ERR_INVALID_VALUE,
+                   "set_inputs: req_list_changed == 0 but no page table is staged (first step, or b2llm_engine_reserve grew "
+                   "the buffers since)");
     }
     e->staged.token_ids = e->in_tokens.as<int64_t>();
     e->staged.seq_starts = e->in_seq_starts.as<int64_t>();
@@ -657,6 +704,8 @@ extern "C" int32_t b2llm_engine_staged_inputs(b2llm_engine* e, const int64_t** t
 
 extern "C" int32_t b2llm_engine_run(b2llm_engine* e, int32_t cache_prefill, float** logits_device, int64_t* logits_stride) {
     B2_REQUIRE(e, B2LLM_ERR_INVALID_VALUE, "null engine");
+    B2_REQUIRE(e->staged.token_ids != nullptr, B2LLM_ERR_INVALID_VALUE,
+               "run: no staged inputs (b2llm_engine_set_inputs must follow b2llm_engine_reserve growth)");
     e->staged.cache_prefill = cache_prefill;
     return b2llm_engine_forward(e, &e->staged, logits_device, logits_stride);
 }
@@ -778,18 +827,28 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
                                    nullptr, e->yl.as<__half>())))
         return rc;
     {
-        Linear head;
-        head.w.p = e->lm_head.p;  // borrowed
-        head.N = d.vocab_size;
-        head.K = h;
+        // vocab-parallel: this rank's column block [B, head_rows] -> all-gather [tp, B, head_rows] -> [B, vocab]
+        float* gemm_out = e->head_split ? e->logits_part.as<float>() : e->logits.as<float>();
+        const int64_t gemm_ld = e->head_rows;
         int32_t r2 = B2LLM_ERR_UNSUPPORTED;
-        Span span(e, 2);
-        if (e->gemm_impl != 1 && gemm_tc_available())
-            r2 = launch_gemm_tc(s, false, e->yl.p, nullptr, head.w.p, nullptr, B, head.N, head.K, EPI_F32, e->logits.p, d.vocab_size);
-        if (r2 == B2LLM_ERR_UNSUPPORTED)
-            r2 = launch_gemm_mma(s, false, e->yl.p, nullptr, head.w.p, nullptr, B, head.N, head.K, EPI_F32, e->logits.p, d.vocab_size);
-        head.w.p = nullptr;
+        {
+            Span span(e, 2);
+            if (e->gemm_impl != 1 && gemm_tc_available())
+                r2 = launch_gemm_tc(s, false, e->yl.p, nullptr, e->lm_head.p, nullptr, B, e->head_rows, h, EPI_F32, gemm_out, gemm_ld);
+            if (r2 == B2LLM_ERR_UNSUPPORTED)
+                r2 = launch_gemm_mma(s, false, e->yl.p, nullptr, e->lm_head.p, nullptr, B, e->head_rows, h, EPI_F32, gemm_out, gemm_ld);
+        }
         if (r2) return r2;
+        if (e->head_split) {
+            Span span(e, 3);
+            load_nccl();
+            B2_REQUIRE(g_nccl_allgather != nullptr && e->comm != nullptr, B2LLM_ERR_UNSUPPORTED,
+                       "tensor parallel: ncclAllGather / communicator unavailable");
+            const int r = g_nccl_allgather(e->logits_part.p, e->logits_gather.p, (size_t)B * e->head_rows, kNcclFloat32, e->comm, s);
+            B2_REQUIRE(r == 0, B2LLM_ERR_DEVICE, "ncclAllGather failed with code " + std::to_string(r));
+            if ((rc = launch_interleave_blocks(s, e->logits_gather.as<float>(), e->tp, B, e->head_rows, e->logits.as<float>())))
+                return rc;
+        }
     }
     e->last_launches = g_launch_count - launches0;
     e->last_tokens = T;

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int nk = Kb / BKB;
+    const int nk = (Kb + BKB - 1) / BKB;  // a partial last k-block reads zeros beyond K (TMA out-of-bounds fill) in A and W
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -372,7 +372,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_m = (M + 2 * BM - 1) / (2 * BM), num_n = N / BN2;
     const int num_tiles = num_m * num_n;
-    const int nk = Kb / BKB;
+    const int nk = (Kb + BKB - 1) / BKB;  // a partial last k-block reads zeros beyond K (TMA out-of-bounds fill) in A and W
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -837,7 +837,7 @@ int32_t launch_gemm_tc(cudaStream_t s, bool is_i8, const void* a, const float* a
     }
     const int Kb = is_i8 ? K : 2 * K;
     // shapes outside the kernel's envelope go to the mma.sync baseline
-    if (Kb % BKB != 0 || N % 32 != 0 || M >= (1ll << 31) || ((uintptr_t)a & 15) || ((uintptr_t)w & 15) ||
+    if (Kb % 16 != 0 || N % 32 != 0 || M >= (1ll << 31) || ((uintptr_t)a & 15) || ((uintptr_t)w & 15) ||
         ((uintptr_t)out & 15) || (ldc % 8) != 0) {
         set_last_error("tcgen05 gemm: shape / alignment outside the kernel envelope");
         return B2LLM_ERR_UNSUPPORTED;

@@ -333,6 +333,16 @@ __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* 
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) st8(out + b * hidden + v * 8, ld8(x + t * hidden + v * 8));
 }
 
+// all-gathered logits [parts, rows, cols] (rank-major, what ncclAllGather delivers) -> [rows, parts * cols]
+__global__ void __launch_bounds__(256) interleave_blocks_kernel(const float4* __restrict__ src, int parts, int64_t rows, int cols4,
+                                                               float4* __restrict__ dst) {
+    const int64_t n = (int64_t)parts * rows * cols4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i % cols4, r = (i / cols4) % rows, p = i / (cols4 * rows);
+        dst[(r * parts + p) * cols4 + c] = src[i];
+    }
+}
+
 // Which row kernel: CTA-per-row wins at decode sizes (rows = running batch ~ 1e3: run 12), the register-resident
 // warp-per-row variants at prefill sizes (65 536 rows: 74 vs 89 ms of norm / quant / rope time per 32-layer step, run 16).
 // Results are bit-identical.  B2LLM_ROW_KERNELS=reg / legacy forces one of them.
@@ -384,6 +394,17 @@ int32_t launch_gather_rows(cudaStream_t s, const __half* x, const int64_t* seq_s
                            __half* out) {
     if (batch == 0) return B2LLM_OK;
     gather_rows_kernel<<<(unsigned)batch, 128, 0, s>>>(x, seq_starts, hidden, out);
+    B2_LAUNCH_CHECK();
+    return B2LLM_OK;
+}
+
+int32_t launch_interleave_blocks(cudaStream_t s, const float* src, int parts, int64_t rows, int cols, float* dst) {
+    B2_REQUIRE(cols % 4 == 0, B2LLM_ERR_INVALID_VALUE, "interleave_blocks: cols must be a multiple of 4");
+    const int64_t n = (int64_t)parts * rows * (cols / 4);
+    if (n == 0) return B2LLM_OK;
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    interleave_blocks_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src), parts, rows, cols / 4,
+                                                    reinterpret_cast<float4*>(dst));
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

@@ -4,8 +4,13 @@
 //
 // One CTA per row.  Greedy (top_k == 1) is one streaming pass: online (max, argmax, sum exp) per
 // thread, merged across the CTA -- 128 KB of logits per row read once.  General top-k stages the
-// row in shared memory when it fits (vocab <= 56 K) and runs k arg-max rounds over it, then one
-// thread applies softmax / top-p / inverse-CDF over the k candidates.
+// row in shared memory when it fits (vocab * 4 B <= 200 KB, i.e. vocab <= 51 200) and runs k arg-max rounds over it,
+// then one thread applies softmax / top-p / inverse-CDF over the k candidates.
+// Guards: a temperature that is not > 0 samples that row greedily from the raw logits (no division by zero); a row
+// without any comparable logit (all NaN) yields token 0 rather than an out-of-range id; top_k <= 0 is rejected on the host.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace b2llm {
@@ -13,6 +18,7 @@ namespace b2llm {
 namespace {
 
 constexpr int kThreads = 512;
+constexpr int64_t kPenaltySlots = 65536;  // batch slots tracked per count map (>= any max_running_batch in use)
 
 struct Best {
     float v;
@@ -59,7 +65,11 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
     __shared__ float sred[64];
     const int b = blockIdx.x;
     const float* row = logits + (int64_t)b * stride;
-    const float T = temps ? temps[b] : 1.0f;
+    float T = temps ? temps[b] : 1.0f;
+    if (!(T > 0.f)) {  // T <= 0 or NaN: greedy on the raw logits
+        T = 1.0f;
+        top_k = 1;
+    }
 
     // pass 1: arg-max + log-sum-exp of l' = l / T
     Best best{-INFINITY, 0x7fffffff};
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
 
     if (top_k <= 1) {
         if (threadIdx.x == 0) {
-            out[b] = top.i;
+            out[b] = (top.i >= 0 && top.i < vocab) ? top.i : 0;
             logprobs[b] = top.v - lse;
         }
         return;
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
             cum = __fadd_rn(cum, __fdiv_rn(expf(cval[i] - c0), sum));
             if (cum > thr) { pick = i; break; }
         }
-        out[b] = cidx[pick];
+        out[b] = (cidx[pick] >= 0 && cidx[pick] < vocab) ? cidx[pick] : 0;
         logprobs[b] = cval[pick] - lse;
     }
 }
@@ -155,10 +165,28 @@ __global__ void __launch_bounds__(256) penalty_kernel(const float* __restrict__ 
                                                      const float* __restrict__ freq, const int64_t* __restrict__ slots,
                                                      const int64_t* __restrict__ tokens, const int64_t* __restrict__ seqstarts,
                                                      const int64_t* __restrict__ start_pos, int vocab,
-                                                     uint16_t* __restrict__ count_map, float* __restrict__ out) {
+                                                     uint16_t* __restrict__ count_map, int64_t* __restrict__ next_pos,
+                                                     float* __restrict__ out) {
     const int b = blockIdx.x;
-    uint16_t* cnt = count_map + slots[b] * (int64_t)vocab;
-    if (start_pos[b] == 0) {
+    const int64_t slot = slots[b];
+    uint16_t* cnt = count_map + slot * (int64_t)vocab;
+    // A slot's counts are cleared on the FIRST step of a request.  start_pos == 0 identifies it only without the prefix
+    // cache: a request admitted on a cache hit enters at start_pos = cache_hit_count (or hit - 1 with a single token,
+    // llm_generator.cc:229-242) and looks like a decode step.  What a continuing request always satisfies is
+    // start_pos == previous start_pos + previous token count (llm_generator.cc:706-717), so the library keeps the
+    // expected next position per slot and clears the row whenever a step does not continue the previous one.
+    __shared__ int s_reset;
+    if (threadIdx.x == 0) {
+        const int64_t sp = start_pos[b];
+        bool reset = sp == 0;
+        if (next_pos != nullptr && slot >= 0 && slot < kPenaltySlots) {
+            reset |= next_pos[slot] != sp;
+            next_pos[slot] = sp + (seqstarts[b + 1] - seqstarts[b]);
+        }
+        s_reset = reset ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_reset) {
         for (int i = threadIdx.x; i < vocab; i += blockDim.x) cnt[i] = 0;
     }
     __syncthreads();
@@ -203,6 +231,10 @@ extern "C" int32_t b2llm_sample_topk_topp(void* stream, const float* logits, con
     B2_REQUIRE(logits && output && logprobs, B2LLM_ERR_INVALID_VALUE, "sample_topk_topp: null pointer");
     B2_REQUIRE(batch >= 0 && vocab_size > 0 && batch_stride >= vocab_size, B2LLM_ERR_INVALID_VALUE,
                "sample_topk_topp: bad shape");
+    // the reference forwards its top_k unchanged (post_processor.cc:133-136, 190-193) and sizes no workspace for
+    // top_k <= 0; "no top-k limit" would need a full-vocabulary sort this kernel does not implement -- refuse loudly
+    // instead of silently sampling greedily
+    B2_REQUIRE(top_k >= 1, B2LLM_ERR_INVALID_VALUE, "sample_topk_topp: top_k must be >= 1 (top_k <= 0 is not supported)");
     B2_REQUIRE(top_k <= 1 || workspace != nullptr, B2LLM_ERR_INVALID_VALUE, "sample_topk_topp: workspace required");
     if (batch == 0) return B2LLM_OK;
     cudaStream_t s = (cudaStream_t)stream;
@@ -211,11 +243,7 @@ extern "C" int32_t b2llm_sample_topk_topp(void* stream, const float* logits, con
     if (top_k > 1 && (size_t)vocab_size * sizeof(float) <= 200 * 1024) {
         smem = (size_t)vocab_size * sizeof(float);
         in_smem = 1;
-        static size_t configured = 0;
-        if (smem > configured) {
-            B2_CHECK_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
-        }
+        B2_ENSURE_DYN_SMEM(sample_kernel, 200 * 1024);  // a per-device attribute (single-process TP: one thread per GPU)
     }
     sample_kernel<<<batch, kThreads, smem, s>>>(logits, temperatures_optional, top_p_optional, rand_device, vocab_size,
                                                 batch_stride, top_k, default_top_p, default_rand, (float*)workspace,
@@ -234,10 +262,28 @@ extern "C" int32_t b2llm_apply_penalty(void* stream, const float* logits_in, con
                    seqstarts && start_pos && penalty_count_map,
                B2LLM_ERR_INVALID_VALUE, "apply_penalty: null pointer");
     if (batch == 0) return B2LLM_OK;
+    // per (device, count map): expected next position of every batch slot, -1 = slot not seen yet
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int64_t*> tracks;
+    int64_t* next_pos = nullptr;
+    {
+        int dev = 0;
+        B2_CHECK_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_pair(dev, (const void*)penalty_count_map);
+        auto it = tracks.find(key);
+        if (it == tracks.end()) {
+            B2_CHECK_CUDA(cudaMalloc(&next_pos, kPenaltySlots * sizeof(int64_t)));
+            B2_CHECK_CUDA(cudaMemsetAsync(next_pos, 0xFF, kPenaltySlots * sizeof(int64_t), (cudaStream_t)stream));
+            tracks[key] = next_pos;
+        } else {
+            next_pos = it->second;
+        }
+    }
     penalty_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(logits_in, temperatures, repetition_penalties,
                                                            presence_penalties_optional, frequency_penalties_optional,
                                                            batch_slots, token_inputs, seqstarts, start_pos, vocab_size,
-                                                           penalty_count_map, logits_out);
+                                                           penalty_count_map, next_pos, logits_out);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
