@@ -11,7 +11,9 @@ What the reference pins (and this file follows):
   * cache_mode 0 (contiguous index) / 1 (page table, INT64_MAX padded)
                                                            src/engine/llm_engine.cc:60-72,
                                                            src/generator/llm_generator.cc:263-298
-  * int8 KV with group 8 is the only quantised cache       src/generator/llm_generator.cc:131-136
+  * int8 KV with group 8 is the only quantised cache; cache_quant_bit 0 / group 1 = fp16 cache
+    without a scale tensor                                 src/generator/llm_generator.cc:131-136,
+                                                           src/backends/cuda/resource_manager.cc:381-388
   * sequences [0, decoding_batches) are in decode phase (one token each), the rest prefill
                                                            src/generator/llm_generator.cc:229-242,706-714
   * logits are fp32 [B, stride>=vocab], one row per sequence (last token)
@@ -132,8 +134,10 @@ def kv_dequant(q8: np.ndarray, s16: np.ndarray, group: int = 8) -> np.ndarray:
 
 # --------------------------------------------------------------------------- KV cache
 class KVCache:
-    """int8 cache + fp16 scale.  Held canonically as [L, 2, T, H, D]; ``export()`` / ``load()``
-    convert to and from the reference's four layouts (llm_engine.cc:118-169):
+    """int8 cache + fp16 scale (``cache_quant_bit`` 8, group 8) or a plain fp16 cache with no scale tensor
+    (``cache_quant_bit`` 0, group 1: llm_generator.cc:131-136; runtime input 10 is then not bound,
+    llm_engine.h:134-136).  Held canonically as [L, 2, T, H, D]; ``export()`` / ``load()`` convert to and from the
+    reference's four layouts (llm_engine.cc:118-169):
 
     layout 0: [T, L, 2, H, D]   1: [L, T, 2, H, D]   2: [L, 2, T, H, D]   3: [L, 2, H, T, D]
     """
@@ -144,16 +148,36 @@ class KVCache:
         self.desc = desc
         self.T = max_tokens
         L, H, D = desc.num_layers, desc.num_kv_heads, desc.head_dim
-        G = D // desc.cache_quant_group
-        self.cache = np.zeros((L, 2, max_tokens, H, D), dtype=np.int8)
+        self.fp16 = desc.cache_quant_bit == 0
+        G = 0 if self.fp16 else D // desc.cache_quant_group
+        self.cache = np.zeros((L, 2, max_tokens, H, D), dtype=np.float16 if self.fp16 else np.int8)
         self.scale = np.zeros((L, 2, max_tokens, H, G), dtype=np.float16)
 
     def write(self, layer, slots, k8, ks, v8, vs):
         slots = np.asarray(slots, dtype=np.int64)
         self.cache[layer, 0, slots] = k8
-        self.scale[layer, 0, slots] = ks
         self.cache[layer, 1, slots] = v8
-        self.scale[layer, 1, slots] = vs
+        if not self.fp16:
+            self.scale[layer, 0, slots] = ks
+            self.scale[layer, 1, slots] = vs
+
+    def append(self, layer, slots, k16, v16):
+        """store this step's (rotated) K and V rows: quantised per group of 8, or as they are (fp16 cache)"""
+        if self.fp16:
+            self.write(layer, slots, k16, None, v16, None)
+            return None
+        g = self.desc.cache_quant_group
+        k8, ks = kv_quant(k16, g)
+        v8, vs = kv_quant(v16, g)
+        self.write(layer, slots, k8, ks, v8, vs)
+        return k8, ks, v8, vs
+
+    def read_values(self, layer, kv, slots):
+        """fp32 values attention sees: fp16(int8 * scale) for the int8 cache, the stored fp16 otherwise"""
+        slots = np.asarray(slots, dtype=np.int64)
+        if self.fp16:
+            return self.cache[layer, kv, slots].astype(F32)
+        return kv_dequant(self.cache[layer, kv, slots], self.scale[layer, kv, slots], self.desc.cache_quant_group)
 
     def read(self, layer, kv, slots):
         slots = np.asarray(slots, dtype=np.int64)
@@ -215,10 +239,8 @@ class Step:
 def attention_decode(q16, cache: KVCache, layer, slots, group):
     """one query token (all heads) against kv_len cached tokens. q16 [Hq, D] -> fp32 [Hq, D]."""
     Hq, D = q16.shape
-    k8, ks = cache.read(layer, 0, slots)
-    v8, vs = cache.read(layer, 1, slots)
-    K = kv_dequant(k8, ks, group)  # [t, Hkv, D]
-    V = kv_dequant(v8, vs, group)
+    K = cache.read_values(layer, 0, slots)  # [t, Hkv, D]
+    V = cache.read_values(layer, 1, slots)
     return _attend(q16.astype(F32)[None], K, V, np.array([K.shape[0] - 1]))[0]
 
 
@@ -336,12 +358,11 @@ class LlamaOracle:
             v = qkv[:, (Hq + Hkv) * D:].reshape(T, Hkv, D)
             q = apply_rope(q, pos, self.cos, self.sin)
             k = apply_rope(k, pos, self.cos, self.sin)
-            k8, ks = kv_quant(k, d.cache_quant_group)
-            v8, vs = kv_quant(v, d.cache_quant_group)
-            self.cache.write(l, slots, k8, ks, v8, vs)
+            appended = self.cache.append(l, slots, k, v)
             if trace is not None and l == 0:
                 trace["l0_q_rot"], trace["l0_k_rot"] = q.copy(), k.copy()
-                trace["l0_k8"], trace["l0_ks"], trace["l0_v8"], trace["l0_vs"] = k8, ks, v8, vs
+                if appended is not None:
+                    trace["l0_k8"], trace["l0_ks"], trace["l0_v8"], trace["l0_vs"] = appended
 
             attn = np.empty((T, Hq, D), dtype=F32)
             for b in range(B):
@@ -355,10 +376,8 @@ class LlamaOracle:
                     Kf, Vf = k[t0:t1].astype(F32), v[t0:t1].astype(F32)
                     if sp > 0:  # cached prefix (prefix-cache hit): dequantised cache for [0, sp)
                         sl = step.slots(d, b, np.arange(sp))
-                        pk8, pks = self.cache.read(l, 0, sl)
-                        pv8, pvs = self.cache.read(l, 1, sl)
-                        Kf = np.concatenate([kv_dequant(pk8, pks, d.cache_quant_group), Kf])
-                        Vf = np.concatenate([kv_dequant(pv8, pvs, d.cache_quant_group), Vf])
+                        Kf = np.concatenate([self.cache.read_values(l, 0, sl), Kf])
+                        Vf = np.concatenate([self.cache.read_values(l, 1, sl), Vf])
                     attn[t0:t1] = _attend(q[t0:t1].astype(F32), Kf, Vf, sp + np.arange(n))
             attn16 = attn.reshape(T, Hq * D).astype(np.float16)
             if ulp_nudge:

@@ -35,6 +35,7 @@ struct PrefillParams {
     int cache_mode, page_size;
     const int8_t* cache;   // layer offset applied
     const __half* scale;   // layer offset applied
+    int kv16;              // fp16 cache (cache_quant_bit 0): cached-prefix rows are copied, not dequantised
     KvStrides cs;
     float sl2;             // log2(e) / sqrt(D)
     __half* out;           // [T, nq * D]
@@ -72,6 +73,12 @@ __device__ __forceinline__ void load_kv_block(const PrefillParams& p, int b, int
         } else {
             const int64_t slot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
             const int64_t off = hk * p.cs.head + slot * p.cs.tok + chunk * 8;
+            if (p.kv16) {
+                const __half* c16 = reinterpret_cast<const __half*>(p.cache) + off;
+                cp_async16(dk, c16, 16);
+                cp_async16(dv, c16 + p.cs.kv, 16);
+                continue;
+            }
 #pragma unroll
             for (int kv = 0; kv < 2; ++kv) {
                 const int64_t o = off + kv * p.cs.kv;
@@ -253,8 +260,9 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(PrefillParams p) {
 
 // attention for the prefill sequences [decoding_batches, batch) of the step (head_dim 128, int8 group-8 cache)
 int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a) {
-    B2_REQUIRE(a.geom.head_dim == 128 && a.geom.quant_group == 8, B2LLM_ERR_UNSUPPORTED,
-               "prefill attention (tensor-core path): head_dim 128 and int8 group-8 cache only");
+    B2_REQUIRE(a.geom.head_dim == 128 && (a.geom.quant_group == 8 || a.geom.quant_group == 1), B2LLM_ERR_UNSUPPORTED,
+               "prefill attention (tensor-core path): head_dim 128; int8 group-8 or fp16 cache");
+    const bool kv16 = a.geom.quant_group == 1;
     const int64_t prefill_seqs = a.step->batch - a.step->decoding_batches;
     if (prefill_seqs <= 0 || a.step->max_seq_len <= 0) return B2LLM_OK;
     B2_REQUIRE(prefill_seqs <= 65535 && a.num_heads <= 65535, B2LLM_ERR_INVALID_VALUE, "too many prefill sequences / heads");
@@ -270,8 +278,9 @@ int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a) {
     p.cache_mode = a.geom.cache_mode;
     p.page_size = a.geom.page_size;
     p.cs = kv_strides(a.geom);
-    p.cache = a.kv_cache + (int64_t)a.layer * p.cs.layer;
-    p.scale = a.kv_scale + (int64_t)a.layer * p.cs.layer / a.geom.quant_group;
+    p.cache = a.kv_cache + (int64_t)a.layer * p.cs.layer * (kv16 ? 2 : 1);
+    p.scale = kv16 ? nullptr : a.kv_scale + (int64_t)a.layer * p.cs.layer / a.geom.quant_group;
+    p.kv16 = kv16 ? 1 : 0;
     p.sl2 = 1.4426950408889634f / sqrtf((float)D);
     p.out = a.out;
     constexpr int smem_bytes = 4 * TILE_BYTES;

@@ -1,5 +1,6 @@
 // K4 + K5 of SURVEY.md section 2.3: rotary embedding on q,k (in place in the qkv activation) and the
-// int8 group-8 quantised append of k,v into the KV cache, for every token of the step.
+// append of k,v into the KV cache, for every token of the step: int8 group-8 quantised (cache_quant_bit 8) or as the
+// fp16 values they are (cache_quant_bit 0 / group 1, llm_generator.cc:131-136: no scale tensor).
 // Eight lanes per (token, head); 16-byte accesses; no shuffles (see the kernel comment).
 //
 // Numeric contract (oracle/llama_ref.py: apply_rope, kv_quant):
@@ -34,7 +35,7 @@ struct RopeKvParams {
 // chunk of the high half (dims [D/2 + 8j, D/2 + 8j + 8)) -- exactly the rotate-half partners, and exactly one
 // quantisation group each, so neither the rotation nor the group max needs a shuffle.  D = 128 uses all 8 lanes
 // of the sub-group, D = 64 the first 4.  A warp covers 4 heads of one token.
-template <int D>
+template <int D, bool KV16>
 __global__ void __launch_bounds__(256) rope_kv_append_kernel(RopeKvParams p) {
     constexpr int HALF = D / 2;
     constexpr int CHUNKS = HALF / 8;  // 16-byte chunks per half: 8 (D = 128) or 4 (D = 64)
@@ -95,6 +96,20 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(RopeKvParams p) {
     const int hk = h - p.nq - kv * p.nkv;
     const int64_t slot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
     const int64_t off = kv * p.cs.kv + hk * p.cs.head + slot * p.cs.tok;
+    if constexpr (KV16) {  // fp16 cache: the (rotated) values as they are; lo / hi were re-rounded to fp16 above
+        __half* crow16 = reinterpret_cast<__half*>(p.cache) + off;
+        uint4 olo, ohi;
+        __half2* a = reinterpret_cast<__half2*>(&olo);
+        __half2* c = reinterpret_cast<__half2*>(&ohi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = __floats2half2_rn(lo[2 * i], lo[2 * i + 1]);
+            c[i] = __floats2half2_rn(hi[2 * i], hi[2 * i + 1]);
+        }
+        *reinterpret_cast<uint4*>(crow16 + 8 * sub) = olo;
+        *reinterpret_cast<uint4*>(crow16 + HALF + 8 * sub) = ohi;
+        return;
+    }
     int8_t* crow = p.cache + off;
     __half* srow = p.scale + off / 8;
 
@@ -125,7 +140,10 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(RopeKvParams p) {
 int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* step, int num_heads,
                               const b2llm_kv_geom& geom, int layer, const float* cos_t, const float* sin_t,
                               int8_t* kv_cache, __half* kv_scale) {
-    B2_REQUIRE(geom.quant_group == 8, B2LLM_ERR_UNSUPPORTED, "kv cache: only int8 with quant group 8 is supported");
+    B2_REQUIRE(geom.quant_group == 8 || geom.quant_group == 1, B2LLM_ERR_UNSUPPORTED,
+               "kv cache: int8 with quant group 8, or fp16 (quant group 1)");
+    const bool kv16 = geom.quant_group == 1;
+    B2_REQUIRE(kv16 || kv_scale != nullptr, B2LLM_ERR_INVALID_VALUE, "kv cache: the int8 cache needs its scale tensor");
     B2_REQUIRE(geom.head_dim == 128 || geom.head_dim == 64, B2LLM_ERR_UNSUPPORTED, "head_dim must be 64 or 128");
     if (step->num_tokens == 0) return B2LLM_OK;
     RopeKvParams p{};
@@ -146,14 +164,17 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
     p.cos_t = cos_t;
     p.sin_t = sin_t;
     p.cs = kv_strides(geom);
-    p.cache = kv_cache + (int64_t)layer * p.cs.layer;
-    p.scale = kv_scale + (int64_t)layer * p.cs.layer / geom.quant_group;
+    p.cache = kv_cache + (int64_t)layer * p.cs.layer * (kv16 ? 2 : 1);
+    p.scale = kv16 ? nullptr : kv_scale + (int64_t)layer * p.cs.layer / geom.quant_group;
     const int64_t threads = step->num_tokens * (num_heads + 2 * geom.num_kv_heads) * 8;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    if (geom.head_dim == 128)
-        rope_kv_append_kernel<128><<<blocks, 256, 0, s>>>(p);
-    else
-        rope_kv_append_kernel<64><<<blocks, 256, 0, s>>>(p);
+    if (geom.head_dim == 128) {
+        if (kv16) rope_kv_append_kernel<128, true><<<blocks, 256, 0, s>>>(p);
+        else rope_kv_append_kernel<128, false><<<blocks, 256, 0, s>>>(p);
+    } else {
+        if (kv16) rope_kv_append_kernel<64, true><<<blocks, 256, 0, s>>>(p);
+        else rope_kv_append_kernel<64, false><<<blocks, 256, 0, s>>>(p);
+    }
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

@@ -474,10 +474,17 @@ int32_t PmxLlama::ForEachWeight(const Sink& sink, std::string* err) {
         rc = sink(kind, layer, p, t->NumElements(), t->name.c_str());
         return rc == 0;
     };
-    // embedding / lm head: whole on every rank in b2llm (the reference gathers them across ranks at run time,
-    // llm_engine.cc:200; here the gather happens once, at load)
+    // lm head split along vocab (rows [r * V/tp, (r+1) * V/tp) per slice): b2llm's head is vocab-parallel too, the
+    // rank's slice goes in as it is and the logits are all-gathered every step (llm_engine.cc:200).
+    // embedding (and an lm head the engine keeps whole: vocab / tp not a multiple of 32, B2LLM_TP_HEAD=whole): whole on
+    // every rank -- a row gather reads only the step's tokens, so nothing is gained by splitting it; assembled once, here.
     auto put_assembled = [&](int32_t kind, const Tensor* mine, int split) -> bool {
         if (split == 0 || tp_ == 1) return put(kind, 0, mine);
+        if (kind == B2LLM_W_LM_HEAD && split == 2) {
+            if (put(kind, 0, mine)) return true;
+            rc = 0;  // the engine keeps the head whole: assemble it below
+            err->clear();
+        }
         full.assign(V * h, 0);
         for (int r = 0; r < tp_; ++r) {
             const Model* m = Sibling(r, err);
