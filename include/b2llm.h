@@ -67,8 +67,9 @@ typedef struct b2llm_model_desc {
     int32_t vocab_size;
     float norm_eps;            /* 1e-5 for LLaMA-2 */
     float rope_theta;          /* 10000 */
-    int32_t cache_quant_bit;   /* 8 (int8 KV, the only quantised mode: llm_generator.cc:131-136) */
-    int32_t cache_quant_group; /* 8 */
+    int32_t cache_quant_bit;   /* 8: int8 KV + fp16 scale per group (the only quantised mode), or 0: fp16 KV, no scale tensor
+                                  (llm_generator.cc:131-136, resource_manager.cc:381-388) */
+    int32_t cache_quant_group; /* 8 with cache_quant_bit 8; 1 with cache_quant_bit 0 */
     int32_t cache_layout;      /* 0..3, llm_engine.cc:118-169 */
     int32_t cache_mode;        /* 0 contiguous index, 1 page table */
     int32_t page_size;         /* tokens per page when cache_mode == 1 */
@@ -160,7 +161,8 @@ B2LLM_API int32_t b2llm_engine_load_weight_shard(b2llm_engine* e, int32_t kind, 
 B2LLM_API int32_t b2llm_engine_random_init(b2llm_engine* e, uint64_t seed);
 
 /* KV memory is owned by the caller (resource_manager.cc:344-362 cudaMalloc's it and
- * llm_engine.h:142-146 SetBufferPtr()s it into inputs 9 / 10). */
+ * llm_engine.h:142-146 SetBufferPtr()s it into inputs 9 / 10).  kv_scale_device is NULL for the fp16 cache
+ * (cache_quant_bit 0: input 10 is not bound, llm_engine.h:134-136). */
 B2LLM_API int32_t b2llm_engine_bind_kv(b2llm_engine* e, void* kv_cache_device, void* kv_scale_device,
                                        uint64_t kv_cache_max_tokens);
 /* bytes per cached token of this rank's slice: cb and sb of resource_manager.cc:381-388 */
@@ -244,7 +246,8 @@ B2LLM_API int32_t b2llm_op_gemm_w8a8(void* stream, const int8_t* a, const float*
 B2LLM_API int32_t b2llm_op_gemm_f16(void* stream, const void* a_fp16, const void* w_fp16, int64_t M, int32_t N,
                                     int32_t K, int32_t epilogue, void* out, int64_t ldc, int32_t impl);
 
-/* KV geometry shared by the cache ops */
+/* KV geometry shared by the cache ops.  quant_group 8 = int8 cache + fp16 scales; quant_group 1 = fp16 cache (kv_cache
+ * points at fp16 elements, kv_scale is NULL) */
 typedef struct b2llm_kv_geom {
     int32_t num_layers, num_kv_heads, head_dim, quant_group;
     int32_t cache_layout, cache_mode, page_size, reserved;

@@ -45,6 +45,7 @@ struct AttnParams {
     int64_t max_pages;
     int nq, nkv, D;
     int cache_mode, page_size, group, cache_prefill;
+    int kv16;              // fp16 cache without scales (cache_quant_bit 0 / group 1); strides stay in ELEMENTS
     const int8_t* cache;   // layer offset applied
     const __half* scale;   // layer offset applied
     KvStrides cs;
@@ -89,14 +90,24 @@ __global__ void __launch_bounds__(128) attn_simple_kernel(AttnParams p) {
         if (j < fresh_from) {
             const int64_t slot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, j);
             const int64_t off = hk * p.cs.head + slot * p.cs.tok;
-            const int8_t* kr = p.cache + off;
-            const int8_t* vr = p.cache + p.cs.kv + off;
-            const float ks = __half2float(p.scale[off / p.group + g]);
-            const float vs = __half2float(p.scale[(p.cs.kv + off) / p.group + g]);
+            if (p.kv16) {
+                const __half* kr = reinterpret_cast<const __half*>(p.cache) + off;
+                const __half* vr = kr + p.cs.kv;
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                kx[i] = __half2float(__float2half_rn(__fmul_rn((float)kr[lane * PER + i], ks)));
-                vx[i] = __half2float(__float2half_rn(__fmul_rn((float)vr[lane * PER + i], vs)));
+                for (int i = 0; i < PER; ++i) {
+                    kx[i] = __half2float(kr[lane * PER + i]);
+                    vx[i] = __half2float(vr[lane * PER + i]);
+                }
+            } else {
+                const int8_t* kr = p.cache + off;
+                const int8_t* vr = p.cache + p.cs.kv + off;
+                const float ks = __half2float(p.scale[off / p.group + g]);
+                const float vs = __half2float(p.scale[(p.cs.kv + off) / p.group + g]);
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    kx[i] = __half2float(__float2half_rn(__fmul_rn((float)kr[lane * PER + i], ks)));
+                    vx[i] = __half2float(__float2half_rn(__fmul_rn((float)vr[lane * PER + i], vs)));
+                }
             }
         } else {
             const int64_t tj = p.seq_starts[b] + (j - sp);
@@ -132,6 +143,7 @@ constexpr int NSTAGE = 3;
 constexpr int K_BYTES = UNIT * 128;      // 2048
 constexpr int S_BYTES = UNIT * 32;       // 512 (16 fp16 scales per token)
 constexpr int STAGE = 2 * K_BYTES + 2 * S_BYTES;  // 5120: K | V | K scales | V scales
+constexpr int STAGE16 = 4 * K_BYTES;     // fp16 cache: K d[0,64) | V d[0,64) | K d[64,128) | V d[64,128), 16 tokens x 128 B each
 constexpr int MAX_WARPS = 4;
 
 struct DecodeTma {          // coordinates of the TMA loader (see make_kv_maps)
@@ -195,40 +207,11 @@ __device__ __forceinline__ float exp2_sel(float x) {
     else return exp2f(x);
 }
 
+// online softmax of one unit's scores + P in the B-operand layout (shared by the int8 and the fp16 cache paths).
+// s_acc: S^T accumulator (rows = tokens g, g + 8; cols = heads 2t, 2t + 1).  Out: P^T fragments as hi + lo fp16 halves.
 template <bool SLIM>
-__device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, const uint32_t (&qb)[8][2], WarpState& st,
-                                             int tbase, int kv_len, float sl2, int g, int t) {
-    const uint8_t* sK = stage;
-    const uint8_t* sV = stage + K_BYTES;
-    const uint8_t* sKS = stage + 2 * K_BYTES;
-    const uint8_t* sVS = sKS + S_BYTES;
-
-    // ---- S^T: lane (g, t) dequantises bytes [32 t, 32 t + 32) of token rows g and g + 8
-    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-        const uint4 ca = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t));
-        const uint4 cb = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t + 1));
-        const uint4 cc = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t));
-        const uint4 cd = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t + 1));
-        const uint2 sc_lo = *reinterpret_cast<const uint2*>(sKS + g * 32 + 8 * t);        // groups 4t .. 4t+3 of token g
-        const uint2 sc_hi = *reinterpret_cast<const uint2*>(sKS + (g + 8) * 32 + 8 * t);  // ... of token g + 8
-        const uint32_t w_lo[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-        const uint32_t w_hi[8] = {cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
-        const __half2 l01 = *reinterpret_cast<const __half2*>(&sc_lo.x), l23 = *reinterpret_cast<const __half2*>(&sc_lo.y);
-        const __half2 h01 = *reinterpret_cast<const __half2*>(&sc_hi.x), h23 = *reinterpret_cast<const __half2*>(&sc_hi.y);
-        const __half2 s_lo[4] = {__low2half2(l01), __high2half2(l01), __low2half2(l23), __high2half2(l23)};
-        const __half2 s_hi[4] = {__low2half2(h01), __high2half2(h01), __low2half2(h23), __high2half2(h23)};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t a0 = deq2(lop3_and_xor(w_lo[j], 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);       // token g, bytes 0,2
-            const uint32_t a2 = deq2(lop3_and_xor(w_lo[j] >> 8, 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);  // token g, bytes 1,3
-            const uint32_t a1 = deq2(lop3_and_xor(w_hi[j], 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);       // token g + 8
-            const uint32_t a3 = deq2(lop3_and_xor(w_hi[j] >> 8, 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);
-            mma_f16_full(s_acc, a0, a1, a2, a3, qb[j][0], qb[j][1]);
-        }
-    }
-
-    // ---- online softmax per head column c (heads 2t + c) over the 16 tokens (rows g and g + 8 of all lanes)
+__device__ __forceinline__ void softmax_unit(const float (&s_acc)[4], WarpState& st, int tbase, int kv_len, float sl2, int g,
+                                             uint32_t& bh0, uint32_t& bh1, uint32_t& bl0, uint32_t& bl1) {
     const bool ok0 = tbase + g < kv_len, ok1 = tbase + g + 8 < kv_len;
     float sv[2][2], pv[2][2];
     bool moved = false;
@@ -266,8 +249,48 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
     __half2 ph0 = __floats2half2_rn(pv[0][0], pv[1][0]), ph1 = __floats2half2_rn(pv[0][1], pv[1][1]);
     const float2 f0 = __half22float2(ph0), f1 = __half22float2(ph1);
     __half2 pl0 = __floats2half2_rn(pv[0][0] - f0.x, pv[1][0] - f0.y), pl1 = __floats2half2_rn(pv[0][1] - f1.x, pv[1][1] - f1.y);
-    const uint32_t bh0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph0)), bh1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph1));
-    const uint32_t bl0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl0)), bl1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl1));
+    bh0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph0));
+    bh1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&ph1));
+    bl0 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl0));
+    bl1 = movmatrix_trans(*reinterpret_cast<uint32_t*>(&pl1));
+}
+
+template <bool SLIM>
+__device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, const uint32_t (&qb)[8][2], WarpState& st,
+                                             int tbase, int kv_len, float sl2, int g, int t) {
+    const uint8_t* sK = stage;
+    const uint8_t* sV = stage + K_BYTES;
+    const uint8_t* sKS = stage + 2 * K_BYTES;
+    const uint8_t* sVS = sKS + S_BYTES;
+
+    // ---- S^T: lane (g, t) dequantises bytes [32 t, 32 t + 32) of token rows g and g + 8
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const uint4 ca = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t));
+        const uint4 cb = *reinterpret_cast<const uint4*>(sK + tile_off(g, 2 * t + 1));
+        const uint4 cc = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t));
+        const uint4 cd = *reinterpret_cast<const uint4*>(sK + tile_off(g + 8, 2 * t + 1));
+        const uint2 sc_lo = *reinterpret_cast<const uint2*>(sKS + g * 32 + 8 * t);        // groups 4t .. 4t+3 of token g
+        const uint2 sc_hi = *reinterpret_cast<const uint2*>(sKS + (g + 8) * 32 + 8 * t);  // ... of token g + 8
+        const uint32_t w_lo[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        const uint32_t w_hi[8] = {cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
+        const __half2 l01 = *reinterpret_cast<const __half2*>(&sc_lo.x), l23 = *reinterpret_cast<const __half2*>(&sc_lo.y);
+        const __half2 h01 = *reinterpret_cast<const __half2*>(&sc_hi.x), h23 = *reinterpret_cast<const __half2*>(&sc_hi.y);
+        const __half2 s_lo[4] = {__low2half2(l01), __high2half2(l01), __low2half2(l23), __high2half2(l23)};
+        const __half2 s_hi[4] = {__low2half2(h01), __high2half2(h01), __low2half2(h23), __high2half2(h23)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t a0 = deq2(lop3_and_xor(w_lo[j], 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);       // token g, bytes 0,2
+            const uint32_t a2 = deq2(lop3_and_xor(w_lo[j] >> 8, 0x00FF00FFu, 0x64806480u), s_lo[j >> 1]);  // token g, bytes 1,3
+            const uint32_t a1 = deq2(lop3_and_xor(w_hi[j], 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);       // token g + 8
+            const uint32_t a3 = deq2(lop3_and_xor(w_hi[j] >> 8, 0x00FF00FFu, 0x64806480u), s_hi[j >> 1]);
+            mma_f16_full(s_acc, a0, a1, a2, a3, qb[j][0], qb[j][1]);
+        }
+    }
+
+    // ---- online softmax per head column c (heads 2t + c) over the 16 tokens (rows g and g + 8 of all lanes)
+    uint32_t bh0, bh1, bl0, bl1;
+    softmax_unit<SLIM>(s_acc, st, tbase, kv_len, sl2, g, bh0, bh1, bl0, bl1);
 
     // ---- O^T += V^T P^T: lane (g, t) dequantises bytes [16 g, 16 g + 16) of token rows {2t, 2t+1, 8+2t, 9+2t}
     const int r0 = 2 * t, r1 = 2 * t + 1, r2 = 8 + 2 * t, r3 = 9 + 2 * t;
@@ -298,6 +321,52 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
     }
 }
 
+// fp16 cache (cache_quant_bit 0): the stage holds four 16-token x 128 B tiles (128 B swizzle): K d[0,64), V d[0,64),
+// K d[64,128), V d[64,128).  No dequantisation: ldmatrix delivers the MMA operands as they lie --
+//     S^T[token, head] = K[token, d] . Q^T[d, head]          A = K rows, natural d order (ldmatrix.x4)
+//     O^T[d, head]    += V^T[d, token] . P^T[token, head]    A = V^T (ldmatrix.x4.trans), m-tile i = d [16 i, 16 i + 16)
+// so accumulator o[i] holds d = 16 i + g (regs 0, 1) and 16 i + 8 + g (regs 2, 3) -- see acc_dim().
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+template <bool SLIM>
+__device__ __forceinline__ void process_unit16(uint32_t stage, const uint32_t (&qb)[8][2], WarpState& st, int tbase, int kv_len,
+                                               float sl2, int g, int lane) {
+    const int mi = lane >> 3, lr = lane & 7;
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    {   // matrices of ldmatrix.x4: (tokens 0-7, chunk c), (tokens 8-15, c), (tokens 0-7, c + 1), (tokens 8-15, c + 1) = a0..a3
+        const int r = lr + (mi & 1) * 8, cofs = mi >> 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t tile = stage + (j < 4 ? 0 : 2 * K_BYTES);
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a0, a1, a2, a3, tile + tile_off(r, (j & 3) * 2 + cofs));
+            mma_f16_full(s_acc, a0, a1, a2, a3, qb[j][0], qb[j][1]);
+        }
+    }
+    uint32_t bh0, bh1, bl0, bl1;
+    softmax_unit<SLIM>(s_acc, st, tbase, kv_len, sl2, g, bh0, bh1, bl0, bl1);
+    {   // .trans matrices: (tokens 0-7, chunk c) -> a0, (tokens 0-7, c + 1) -> a1, (tokens 8-15, c) -> a2, (tokens 8-15, c + 1) -> a3
+        const int r = lr + (mi >> 1) * 8, cofs = mi & 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t tile = stage + K_BYTES + (i < 4 ? 0 : 2 * K_BYTES);
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4_trans(a0, a1, a2, a3, tile + tile_off(r, (i & 3) * 2 + cofs));
+            mma_f16_full(st.o[i], a0, a1, a2, a3, bh0, bh1);
+            mma_f16_full(st.o[i], a0, a1, a2, a3, bl0, bl1);
+        }
+    }
+}
+
+// head-dim index held by accumulator register pair `hi` (0: regs 0,1; 1: regs 2,3) of m-tile i in lane group g
+template <bool KV16>
+__device__ __forceinline__ int acc_dim(int i, int g, int hi) {
+    return KV16 ? 16 * i + 8 * hi + g : 16 * g + 8 * hi + i;
+}
+
 // G: q heads per CTA (rows of the MMA M dimension in use), 1..8.  LOADER: 0 cp.async, 1 TMA, 2 TMA "slim" -- same
 // data path and arithmetic as 1 with fewer instructions per unit around it: the page table is walked incrementally
 // (no integer division per unit in the issuing lane) and exp2 is a bare ex2.approx.  The kernel's time follows the
@@ -305,11 +374,14 @@ __device__ __forceinline__ void process_unit(const uint8_t* __restrict__ stage, 
 // LOADER 3 (default for cache layouts 2 / 3 since round 2 run 1): slim + K and V of a unit in ONE 4-D TMA box
 // {row bytes, 16 tokens, 1 head, 2 (k, v)} and their scales in another -- 2 bulk loads per unit instead of 4
 // (cache layouts 2 and 3, where k / v is an outer dimension; the smem image is unchanged: K | V | K scales | V scales).
-template <int G, int WARPS, int LOADER>
+// KV16: fp16 cache without scales (cache_quant_bit 0): 8 KB stages of four 128 B-swizzled tiles, ldmatrix operands
+// (process_unit16); same ring, walk, softmax, split and merge code.
+template <int G, int WARPS, int LOADER, bool KV16>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
                        DecodeTma tc) {
     constexpr bool TMA = LOADER != 0, SLIM = LOADER >= 2, MERGED = LOADER == 3;
+    constexpr int STG = KV16 ? STAGE16 : STAGE;  // bytes per ring stage
     extern __shared__ uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -322,7 +394,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024 B alignment
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + WARPS * NSTAGE * STAGE;
+    const uint32_t bars = smem_base + WARPS * NSTAGE * STG;
 
     const int kv_len = (int)(p.start_pos[b] + 1);
     const int units_total = (kv_len + UNIT - 1) / UNIT;
@@ -351,7 +423,10 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int base = 32 * t + 4 * j;
-            if (g < nrow) {
+            if (g < nrow && KV16) {  // natural k order: step j covers d = [16 j, 16 j + 16)
+                qa[j][0] = *reinterpret_cast<const uint32_t*>(qrow + 16 * j + 2 * t);
+                qa[j][1] = *reinterpret_cast<const uint32_t*>(qrow + 16 * j + 8 + 2 * t);
+            } else if (g < nrow) {
                 const uint2 v = *reinterpret_cast<const uint2*>(qrow + base);  // halves d..d+3
                 qa[j][0] = prmt(v.x, v.y, 0x5410);  // (d+0, d+2)
                 qa[j][1] = prmt(v.x, v.y, 0x7632);  // (d+1, d+3)
@@ -362,8 +437,8 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         }
     }
 
-    uint8_t* wsm = smem + warp * (NSTAGE * STAGE);
-    const uint32_t wsm_u32 = smem_base + warp * (NSTAGE * STAGE);
+    uint8_t* wsm = smem + warp * (NSTAGE * STG);
+    const uint32_t wsm_u32 = smem_base + warp * (NSTAGE * STG);
     const uint32_t wbar = bars + 8u * (warp * NSTAGE);
 
     // page-table walk: first cache slot of unit u (its 16 tokens are contiguous slots on the TMA path)
@@ -402,13 +477,58 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     };
 
     // ---- loader: fill stage `st` of this warp's ring with unit u
-    const int8_t* kbase = p.cache + hk * p.cs.head;
-    const int8_t* vbase = kbase + p.cs.kv;
-    const __half* ksbase = p.scale + hk * p.cs.head / 8;
-    const __half* vsbase = ksbase + p.cs.kv / 8;
+    constexpr int ESZ = KV16 ? 2 : 1;  // bytes per cache element
+    const int8_t* kbase = p.cache + hk * p.cs.head * ESZ;
+    const int8_t* vbase = kbase + p.cs.kv * ESZ;
+    const __half* ksbase = KV16 ? nullptr : p.scale + hk * p.cs.head / 8;
+    const __half* vsbase = KV16 ? nullptr : ksbase + p.cs.kv / 8;
     auto load_unit = [&](int u, int st) {
-        const uint32_t sK = wsm_u32 + st * STAGE, sV = sK + K_BYTES, sKS = sV + K_BYTES, sVS = sKS + S_BYTES;
-        if constexpr (TMA) {
+        const uint32_t sK = wsm_u32 + st * STG, sV = sK + K_BYTES, sKS = sV + K_BYTES, sVS = sKS + S_BYTES;
+        if constexpr (TMA && KV16) {
+            // tiles K lo | V lo | K hi | V hi: the box is 128 B wide (one swizzle span), a row of the fp16 cache 256 B
+            if (lane == 0) {
+                const int s0 = SLIM ? (int)walk_slot0() : (int)unit_slot0(u);
+                const uint32_t bar = wbar + 8u * st;
+                mbar_expect_tx(bar, STAGE16);
+                if constexpr (MERGED) {  // {128 B, 16 tokens, 1 head, (k, v)}: K and V halves in one load
+                    if (tc.tok_dim == 1) {
+                        tma_load_4d(sK, &map_kv, bar, 0, s0, hk, tc.k_fixed);
+                        tma_load_4d(sK + 2 * K_BYTES, &map_kv, bar, 128, s0, hk, tc.k_fixed);
+                    } else {
+                        tma_load_4d(sK, &map_kv, bar, 0, hk, s0, tc.k_fixed);
+                        tma_load_4d(sK + 2 * K_BYTES, &map_kv, bar, 128, hk, s0, tc.k_fixed);
+                    }
+                } else {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t dk = sK + hf * 2 * K_BYTES, dv = dk + K_BYTES;
+                        if (tc.tok_dim == 1) {
+                            tma_load_3d(dk, &map_kv, bar, 128 * hf, tc.k_tok0 + s0, tc.k_fixed + hk);
+                            tma_load_3d(dv, &map_kv, bar, 128 * hf, tc.v_tok0 + s0, tc.v_fixed + hk);
+                        } else {
+                            tma_load_3d(dk, &map_kv, bar, 128 * hf, tc.k_fixed + hk, tc.k_tok0 + s0);
+                            tma_load_3d(dv, &map_kv, bar, 128 * hf, tc.v_fixed + hk, tc.v_tok0 + s0);
+                        }
+                    }
+                }
+            }
+        } else if constexpr (KV16) {
+            // cp.async: 16 tokens x (16 K chunks + 16 V chunks) of 16 B; lane = chunk column, one token row per pass
+            int64_t myslot = -1;
+            {
+                const int pos = u * UNIT + (lane & 15);
+                if (pos < kv_len) myslot = kv_slot(p.cache_indices, p.cache_mode, p.page_size, p.max_pages, b, pos);
+            }
+            const int kvsel = lane >> 4, c = lane & 15;  // lanes 0-15: K chunks, 16-31: V chunks
+            const uint32_t dst_tile = sK + kvsel * K_BYTES + (c >> 3) * 2 * K_BYTES;
+            const int8_t* src_base = (kvsel ? vbase : kbase) + c * 16;
+#pragma unroll 4
+            for (int r = 0; r < UNIT; ++r) {
+                const int64_t slot = __shfl_sync(0xffffffffu, myslot, r);
+                const int ok = slot >= 0 ? 16 : 0;
+                cp_async16(dst_tile + tile_off(r, c & 7), src_base + (slot >= 0 ? slot : 0) * p.cs.tok * 2, ok);
+            }
+        } else if constexpr (TMA) {
             if (lane == 0) {
                 const int s0 = SLIM ? (int)walk_slot0() : (int)unit_slot0(u);
                 const uint32_t bar = wbar + 8u * st;
@@ -494,7 +614,22 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
             if constexpr (SLIM) walk_advance();
             u_issue += WARPS;
         }
-        uint8_t* stage = wsm + stg * STAGE;
+        uint8_t* stage = wsm + stg * STG;
+        if constexpr (KV16) {
+            // the tail unit's rows past kv_len hold whatever the cache holds there: zero their V rows
+            // (their scores are masked to -inf in softmax_unit; 0 * NaN must not reach the accumulator)
+            const int valid = kv_len - u * UNIT;
+            if (valid < UNIT) {
+                for (int idx = lane; idx < (UNIT - valid) * 16; idx += 32) {
+                    const int r = valid + (idx >> 4), c = idx & 15;
+                    *reinterpret_cast<uint4*>(stage + K_BYTES + (c >> 3) * 2 * K_BYTES + tile_off(r, c & 7)) = make_uint4(0, 0, 0, 0);
+                }
+                __syncwarp();
+            }
+            process_unit16<SLIM>(wsm_u32 + stg * STG, qa, st, u * UNIT, kv_len, sl2, g, lane);
+            if (++stg == NSTAGE) { stg = 0; phase ^= 1; }
+            continue;
+        }
         if constexpr (TMA) {
             // the tail unit's rows past kv_len hold whatever the cache holds there: neutralise their V scales
             // (their scores are masked to -inf below; 0 * NaN must not reach the accumulator)
@@ -527,7 +662,15 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
             const int rq = 2 * t + c;
             if (rq >= nrow) continue;
             const int hq = hq0 + rq;
-            if (p.nsplit == 1) {
+            if (p.nsplit == 1 && KV16) {
+                const float inv = 1.f / st.l_run[c];
+                __half* dst = p.out + tok * (int64_t)p.nq * 128 + (int64_t)hq * 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    dst[acc_dim<true>(i, g, 0)] = __float2half_rn(st.o[i][c] * inv);
+                    dst[acc_dim<true>(i, g, 1)] = __float2half_rn(st.o[i][2 + c] * inv);
+                }
+            } else if (p.nsplit == 1) {
                 const float inv = 1.f / st.l_run[c];
                 uint32_t pk[8];
 #pragma unroll
@@ -544,8 +687,8 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
                 float* wrow = p.ws + (((int64_t)b * p.nq + hq) * p.nsplit + split) * 130;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    wrow[16 * g + i] = st.o[i][c];
-                    wrow[16 * g + 8 + i] = st.o[i][2 + c];
+                    wrow[acc_dim<KV16>(i, g, 0)] = st.o[i][c];
+                    wrow[acc_dim<KV16>(i, g, 1)] = st.o[i][2 + c];
                 }
                 if (g == 0) {
                     wrow[128] = st.m_run[c];
@@ -564,8 +707,8 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         float* row = red + (warp * G + rq) * 130;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            row[16 * g + i] = st.o[i][c];
-            row[16 * g + 8 + i] = st.o[i][2 + c];
+            row[acc_dim<KV16>(i, g, 0)] = st.o[i][c];
+            row[acc_dim<KV16>(i, g, 1)] = st.o[i][2 + c];
         }
         if (g == 0) {
             row[128] = st.m_run[c];
@@ -651,8 +794,9 @@ AttnParams make_params(const AttnArgs& a) {
     p.group = a.geom.quant_group;
     p.cache_prefill = a.step->cache_prefill;
     p.cs = kv_strides(a.geom);
-    p.cache = a.kv_cache + (int64_t)a.layer * p.cs.layer;
-    p.scale = a.kv_scale + (int64_t)a.layer * p.cs.layer / a.geom.quant_group;
+    p.kv16 = a.geom.quant_group == 1 ? 1 : 0;
+    p.cache = a.kv_cache + (int64_t)a.layer * p.cs.layer * (p.kv16 ? 2 : 1);
+    p.scale = p.kv16 ? nullptr : a.kv_scale + (int64_t)a.layer * p.cs.layer / a.geom.quant_group;
     p.sm_scale = 1.0f / sqrtf((float)a.geom.head_dim);
     p.out = a.out;
     p.ws = reinterpret_cast<float*>(a.workspace);
@@ -675,8 +819,9 @@ std::map<std::tuple<const void*, const void*, int, int, int, int, uint64_t>, KvM
 
 bool make_kv_maps(const AttnArgs& a, KvMaps* out) {
     const b2llm_kv_geom& g = a.geom;
+    const bool kv16 = g.quant_group == 1;
     auto key = std::make_tuple((const void*)a.kv_cache, (const void*)a.kv_scale, g.cache_layout, g.num_layers, g.num_kv_heads,
-                               g.head_dim, (uint64_t)g.max_tokens);
+                               g.head_dim * (kv16 ? 2 : 1), (uint64_t)g.max_tokens);
     std::lock_guard<std::mutex> lk(g_kvmap_mutex);
     auto it = g_kvmap_cache.find(key);
     if (it != g_kvmap_cache.end()) {
@@ -684,8 +829,9 @@ bool make_kv_maps(const AttnArgs& a, KvMaps* out) {
         return true;
     }
     const uint64_t L = g.num_layers, H = g.num_kv_heads, T = g.max_tokens;
-    for (int which = 0; which < 2; ++which) {
-        const uint64_t rb = which == 0 ? 128 : 32;  // row bytes: int8 values / fp16 scales
+    for (int which = 0; which < (kv16 ? 1 : 2); ++which) {
+        // row bytes: int8 values (fp16 cache: 256 B rows read as two 128 B boxes) / fp16 scales
+        const uint64_t rb = which == 0 ? (kv16 ? 256 : 128) : 32;
         uint64_t dims[3], strides[2];
         uint32_t box[3];
         dims[0] = rb;
@@ -695,13 +841,14 @@ bool make_kv_maps(const AttnArgs& a, KvMaps* out) {
             case 1: dims[1] = 2 * H; dims[2] = L * T; box[1] = 1; box[2] = UNIT; break;
             default: dims[1] = L * 2 * H; dims[2] = T; box[1] = 1; box[2] = UNIT; break;
         }
-        box[0] = (uint32_t)rb;
+        box[0] = (uint32_t)(rb > 128 ? 128 : rb);
         strides[0] = rb;
         strides[1] = rb * dims[1];
         if (!tma_encode_bytes(which == 0 ? &out->kv : &out->sc, which == 0 ? (const void*)a.kv_cache : (const void*)a.kv_scale,
                               3, dims, strides, box, which == 0))
             return false;
     }
+    if (kv16) out->sc = out->kv;  // no scale tensor: the kernel never touches this map
     if (g_kvmap_cache.size() > 64) g_kvmap_cache.clear();
     g_kvmap_cache[key] = *out;
     return true;
@@ -715,8 +862,9 @@ std::map<std::tuple<const void*, const void*, int, int, int, int, uint64_t>, KvM
 bool make_kv_maps_merged(const AttnArgs& a, KvMaps* out) {
     const b2llm_kv_geom& g = a.geom;
     if (g.cache_layout != 2 && g.cache_layout != 3) return false;
+    const bool kv16 = g.quant_group == 1;
     auto key = std::make_tuple((const void*)a.kv_cache, (const void*)a.kv_scale, g.cache_layout, g.num_layers, g.num_kv_heads,
-                               g.head_dim, (uint64_t)g.max_tokens);
+                               g.head_dim * (kv16 ? 2 : 1), (uint64_t)g.max_tokens);
     std::lock_guard<std::mutex> lk(g_kvmap_mutex);
     auto it = g_kvmap4_cache.find(key);
     if (it != g_kvmap4_cache.end()) {
@@ -724,13 +872,13 @@ bool make_kv_maps_merged(const AttnArgs& a, KvMaps* out) {
         return true;
     }
     const uint64_t L = g.num_layers, H = g.num_kv_heads, T = g.max_tokens;
-    for (int which = 0; which < 2; ++which) {
-        const uint64_t rb = which == 0 ? 128 : 32;
+    for (int which = 0; which < (kv16 ? 1 : 2); ++which) {
+        const uint64_t rb = which == 0 ? (kv16 ? 256 : 128) : 32;
         uint64_t dims[4], strides[3];
         uint32_t box[4];
         dims[0] = rb;
         dims[3] = L * 2;
-        box[0] = (uint32_t)rb;
+        box[0] = (uint32_t)(rb > 128 ? 128 : rb);
         box[3] = 2;
         if (g.cache_layout == 3) {
             dims[1] = T; dims[2] = H; box[1] = UNIT; box[2] = 1;
@@ -744,6 +892,7 @@ bool make_kv_maps_merged(const AttnArgs& a, KvMaps* out) {
                               4, dims, strides, box, which == 0))
             return false;
     }
+    if (kv16) out->sc = out->kv;
     if (g_kvmap4_cache.size() > 64) g_kvmap4_cache.clear();
     g_kvmap4_cache[key] = *out;
     return true;
@@ -783,7 +932,8 @@ int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
 }
 
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end) {
-    B2_REQUIRE(a.geom.quant_group == 8, B2LLM_ERR_UNSUPPORTED, "kv cache: only int8 with quant group 8 is supported");
+    B2_REQUIRE(a.geom.quant_group == 8 || a.geom.quant_group == 1, B2LLM_ERR_UNSUPPORTED,
+               "kv cache: int8 with quant group 8, or fp16 (quant group 1)");
     if (token_end <= token_begin) return B2LLM_OK;
     AttnParams p = make_params(a);
     p.token_begin = token_begin;
@@ -802,11 +952,12 @@ int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token
     return B2LLM_OK;
 }
 
-template <int G, int WARPS, int LOADER>
+template <int G, int WARPS, int LOADER, bool KV16 = false>
 static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc) {
-    auto kern = attn_decode_kernel<G, WARPS, LOADER>;
-    constexpr int smem_bytes = WARPS * NSTAGE * STAGE + 1024 + 8 * WARPS * NSTAGE + 64 +
-                               (WARPS * G * 130 * 4 > WARPS * NSTAGE * STAGE ? WARPS * G * 130 * 4 : 0);
+    auto kern = attn_decode_kernel<G, WARPS, LOADER, KV16>;
+    constexpr int STG = KV16 ? STAGE16 : STAGE;
+    constexpr int smem_bytes = WARPS * NSTAGE * STG + 1024 + 8 * WARPS * NSTAGE + 64 +
+                               (WARPS * G * 130 * 4 > WARPS * NSTAGE * STG ? WARPS * G * 130 * 4 : 0);
     B2_ENSURE_DYN_SMEM(kern, smem_bytes);
     const int gq = p.nq / p.nkv;
     const int chunks = (gq + G - 1) / G;
@@ -824,6 +975,21 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
 template <int G>
 static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc, int warps, bool tma,
                                int slim) {
+    if (p.kv16) {  // fp16 cache: merged / slim TMA loaders or cp.async
+        if (tma && slim == 2) {
+            if (warps == 1) return launch_decode<G, 1, 3, true>(s, p, maps, tc);
+            if (warps == 2) return launch_decode<G, 2, 3, true>(s, p, maps, tc);
+            return launch_decode<G, 4, 3, true>(s, p, maps, tc);
+        }
+        if (tma) {
+            if (warps == 1) return launch_decode<G, 1, 2, true>(s, p, maps, tc);
+            if (warps == 2) return launch_decode<G, 2, 2, true>(s, p, maps, tc);
+            return launch_decode<G, 4, 2, true>(s, p, maps, tc);
+        }
+        if (warps == 1) return launch_decode<G, 1, 0, true>(s, p, maps, tc);
+        if (warps == 2) return launch_decode<G, 2, 0, true>(s, p, maps, tc);
+        return launch_decode<G, 4, 0, true>(s, p, maps, tc);
+    }
     if (tma && slim == 2) {
         if (warps == 1) return launch_decode<G, 1, 3>(s, p, maps, tc);
         if (warps == 2) return launch_decode<G, 2, 3>(s, p, maps, tc);
@@ -845,8 +1011,8 @@ static int32_t dispatch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps
 }
 
 int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
-    B2_REQUIRE(a.geom.head_dim == 128 && a.geom.quant_group == 8, B2LLM_ERR_UNSUPPORTED,
-               "attention (tensor-core path): head_dim 128 and int8 group-8 cache only");
+    B2_REQUIRE(a.geom.head_dim == 128 && (a.geom.quant_group == 8 || a.geom.quant_group == 1), B2LLM_ERR_UNSUPPORTED,
+               "attention (tensor-core path): head_dim 128; int8 group-8 or fp16 cache");
     B2_REQUIRE(a.step->decoding_batches <= 65535, B2LLM_ERR_INVALID_VALUE, "too many decoding sequences");
     if (a.step->decoding_batches == 0) return B2LLM_OK;
     std::call_once(g_attn_env_once, [] {

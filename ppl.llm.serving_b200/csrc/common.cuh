@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/b2llm.h"
 
@@ -218,6 +219,29 @@ int32_t launch_attention_prefill_tc(cudaStream_t s, const AttnArgs& a);
 // else the mma.sync kernel
 int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, bool force_tc = false);  // sequences [decoding_batches, batch)
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim);
+
+// ---- tensor-parallel fused residual join over NVLink peer memory (tp_join.cu)
+constexpr int kTpMaxRanks = 8;
+struct TpPeers {            // every rank's communication buffer as mapped into THIS process / device
+    int tp, rank;
+    uint8_t* base[kTpMaxRanks];
+};
+struct TpLayout {           // byte offsets inside a communication buffer (identical on all ranks)
+    size_t flags;           // 64 flag words + CTA counter + fault word
+    size_t partial;         // fp16 [tokens, hidden]: this rank's row-parallel GEMM output
+    size_t x;               // fp16 [tokens, hidden]: residual stream
+    size_t q, qscale;       // int8 [tokens, act_cols] + fp32 [tokens]: quantised GEMM input
+    size_t y;               // fp16 [tokens, hidden]: unquantised GEMM input (fp16 / W4A16 weights)
+    size_t total;
+};
+TpLayout tp_layout(int64_t max_tokens, int hidden, int act_cols);
+// mode 0: residual join only, 1: + RMSNorm -> int8 + scale, 2: + RMSNorm -> fp16; bcast_x: every rank gets the new x rows
+int32_t launch_tp_join(cudaStream_t s, const TpPeers& peers, const TpLayout& L, int mode, bool bcast_x, const __half* gamma,
+                       float eps, int64_t rows, int hidden, uint32_t epoch);
+// collective over the engine's NCCL communicator: publish `local`, map every peer's buffer (peer access inside one
+// process, CUDA IPC across processes; mappings opened through IPC are appended to *ipc_opened for cudaIpcCloseMemHandle)
+int32_t tp_comm_exchange(cudaStream_t s, void* nccl_comm, int (*allgather)(const void*, void*, size_t, int, void*, cudaStream_t),
+                         int rank, int tp, void* local, TpPeers* out, std::vector<void*>* ipc_opened);
 
 int32_t launch_synth_fp16(cudaStream_t s, uint64_t seed, uint64_t tid, uint64_t n, float std, float mean, __half* out);
 int32_t launch_synth_fp16_2d(cudaStream_t s, uint64_t seed, uint64_t tid, int64_t rows, int64_t cols, int64_t row0,

@@ -43,9 +43,17 @@ constexpr int kNcclFloat16 = 6, kNcclFloat32 = 7, kNcclSum = 0;
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool owned = true;
+    void view(void* ptr, size_t n) {  // a window of memory somebody else owns (the TP communication buffer)
+        release();
+        p = ptr;
+        bytes = n;
+        owned = false;
+    }
     int32_t ensure(size_t n) {
         if (n <= bytes) return B2LLM_OK;
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
+        owned = true;
         p = nullptr;
         bytes = 0;
         if (cudaMalloc(&p, n) != cudaSuccess) {
@@ -57,9 +65,10 @@ struct DevBuf {
         return B2LLM_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         bytes = 0;
+        owned = true;
     }
     template <class T>
     T* as() const { return reinterpret_cast<T*>(p); }
@@ -101,6 +110,16 @@ struct b2llm_engine {
     bool head_split = false;
     int head_rows = 0;
     DevBuf logits_part, logits_gather;
+    // tp > 1: fused residual join over NVLink peer memory (tp_join.cu).  tmp / x / a8 / a_s / y16 are windows of `comm`,
+    // which every peer maps; B2LLM_TP_JOIN=nccl keeps ncclAllReduce + separate norm kernels (the cross-check path)
+    bool tp_fused = false;
+    bool comm_mapped = false;
+    DevBuf cbuf;                       // the peer-mapped communication buffer
+    std::vector<void*> comm_retired;   // outgrown buffers: peers may still map them, freed with the engine
+    std::vector<void*> ipc_opened;
+    TpLayout comm_layout{};
+    TpPeers peers{};
+    uint32_t epoch = 0;
     // staged inputs
     DevBuf in_tokens, in_seq_starts, in_kv_starts, in_start_pos, in_cache_idx;
     b2llm_step staged{};
@@ -212,6 +231,27 @@ int32_t allreduce_half(b2llm_engine* e, __half* buf, size_t count) {
     return B2LLM_OK;
 }
 
+// (re)publish this rank's communication buffer and map the peers' (collective: every rank of the group calls it in the
+// same step -- buffer sizes follow the step sizes, which are identical on all ranks, llm_engine.cc:179)
+int32_t map_comm(b2llm_engine* e) {
+    load_nccl();
+    B2_REQUIRE(g_nccl_allgather != nullptr && e->comm != nullptr, B2LLM_ERR_UNSUPPORTED,
+               "tensor parallel: ncclAllGather / communicator unavailable");
+    for (void* m : e->ipc_opened) cudaIpcCloseMemHandle(m);
+    e->ipc_opened.clear();
+    B2_CHECK_CUDA(cudaMemsetAsync(e->cbuf.p, 0, 1024, e->stream));  // flags, CTA counter, fault word
+    const int32_t rc = tp_comm_exchange(e->stream, e->comm, g_nccl_allgather, e->rank, e->tp, e->cbuf.p, &e->peers, &e->ipc_opened);
+    if (rc) return rc;
+    e->epoch = 0;
+    e->comm_mapped = true;
+    return B2LLM_OK;
+}
+
+int32_t tp_join(b2llm_engine* e, int mode, bool bcast_x, const __half* gamma, int64_t T) {
+    Span span(e, 3);
+    return launch_tp_join(e->stream, e->peers, e->comm_layout, mode, bcast_x, gamma, e->d.norm_eps, T, e->d.hidden_dim, ++e->epoch);
+}
+
 }  // namespace
 
 extern "C" const char* b2llm_version(void) { return "b2llm 0.1 (sm_100a)"; }
@@ -243,8 +283,10 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
     B2_REQUIRE(d.num_kv_heads > 0 && d.num_heads % d.num_kv_heads == 0, B2LLM_ERR_INVALID_VALUE, "bad num_kv_heads");
     B2_REQUIRE(d.num_heads % tp == 0 && d.num_kv_heads % tp == 0 && d.intermediate_dim % tp == 0, B2LLM_ERR_INVALID_VALUE,
                "heads / kv heads / intermediate_dim must divide by tensor_parallel_size");
-    B2_REQUIRE(d.cache_quant_bit == 8 && d.cache_quant_group == 8, B2LLM_ERR_UNSUPPORTED,
-               "only the int8 group-8 KV cache is implemented");
+    // the two cache modes the reference accepts (llm_generator.cc:131-136): int8 with an fp16 scale per 8 elements, or
+    // plain fp16 without a scale tensor (bit 0, group 1)
+    B2_REQUIRE((d.cache_quant_bit == 8 && d.cache_quant_group == 8) || (d.cache_quant_bit == 0 && d.cache_quant_group == 1),
+               B2LLM_ERR_UNSUPPORTED, "KV cache: (cache_quant_bit 8, cache_quant_group 8) or (cache_quant_bit 0, cache_quant_group 1)");
     B2_REQUIRE(d.cache_layout >= 0 && d.cache_layout <= 3, B2LLM_ERR_INVALID_VALUE, "cache_layout must be 0..3");
     B2_REQUIRE(d.cache_mode == 0 || (d.cache_mode == 1 && d.page_size > 0), B2LLM_ERR_INVALID_VALUE,
                "cache_mode must be 0, or 1 with page_size > 0");
@@ -293,6 +335,10 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
             e->head_split = true;
             e->head_rows = d.vocab_size / tp;
         }
+    }
+    if (tp > 1 && tp <= kTpMaxRanks && d.hidden_dim % 8 == 0 && d.hidden_dim <= 8192) {
+        const char* js = getenv("B2LLM_TP_JOIN");
+        e->tp_fused = !(js && js[0] == 'n');
     }
     if (const char* s = getenv("B2LLM_ATTN_IMPL")) e->attn_impl = atoi(s);
     if (const char* s = getenv("B2LLM_GEMM_IMPL")) e->gemm_impl = atoi(s);
@@ -357,16 +403,35 @@ extern "C" int32_t b2llm_engine_reserve(b2llm_engine* e, int64_t max_tokens, int
     int32_t rc = B2LLM_OK;
     auto chk = [&](int32_t r) { if (rc == B2LLM_OK) rc = r; };
     const size_t amax_cols = (size_t)(h > e->nq * e->D ? h : e->nq * e->D);
-    chk(e->x.ensure(T * h * 2));
-    chk(e->a8.ensure(T * amax_cols));
-    chk(e->a_s.ensure(T * 4));
+    if (e->tp_fused) {
+        // one allocation every peer maps; the old one (if any) is retired, not freed: peers may still hold its mapping
+        const TpLayout L = tp_layout((int64_t)T, h, (int)amax_cols);
+        if (e->cbuf.p) e->comm_retired.push_back(e->cbuf.p);
+        e->cbuf.p = nullptr;
+        e->cbuf.bytes = 0;
+        chk(e->cbuf.ensure(L.total));
+        if (rc == B2LLM_OK) {
+            uint8_t* base = (uint8_t*)e->cbuf.p;
+            e->comm_layout = L;
+            e->comm_mapped = false;
+            e->tmp.view(base + L.partial, T * h * 2);
+            e->x.view(base + L.x, T * h * 2);
+            e->a8.view(base + L.q, T * amax_cols);
+            e->a_s.view(base + L.qscale, T * 4);
+            e->y16.view(base + L.y, T * h * 2);
+        }
+    } else {
+        chk(e->x.ensure(T * h * 2));
+        chk(e->a8.ensure(T * amax_cols));
+        chk(e->a_s.ensure(T * 4));
+    }
     chk(e->qkv.ensure(T * e->nqkv * 2));
     chk(e->attn.ensure(T * e->nq * e->D * 2));
     chk(e->act.ensure(T * e->inter * 2));
     chk(e->b8.ensure(T * e->inter));
     chk(e->b_s.ensure(T * 4));
-    if (e->tp > 1) chk(e->tmp.ensure(T * h * 2));
-    if (!i8 || e->tp > 1) chk(e->y16.ensure(T * h * 2));
+    if (e->tp > 1 && !e->tp_fused) chk(e->tmp.ensure(T * h * 2));
+    if ((!i8 || e->tp > 1) && !e->tp_fused) chk(e->y16.ensure(T * h * 2));
     chk(e->xl.ensure(B * h * 2));
     chk(e->yl.ensure(B * h * 2));
     chk(e->logits.ensure(B * (size_t)d.vocab_size * 4));
@@ -417,6 +482,9 @@ extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
             b->release();
     }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    for (void* m : e->ipc_opened) cudaIpcCloseMemHandle(m);
+    for (void* m : e->comm_retired) cudaFree(m);
+    e->cbuf.release();
     for (DevBuf* b : {&e->embedding, &e->final_norm, &e->lm_head, &e->rope_cos, &e->rope_sin, &e->x, &e->a8, &e->a_s,
                       &e->qkv, &e->attn, &e->act, &e->b8, &e->b_s, &e->tmp, &e->y16, &e->xl, &e->yl, &e->logits,
                       &e->attn_ws, &e->w16_scratch, &e->logits_part, &e->logits_gather, &e->in_tokens, &e->in_seq_starts, &e->in_kv_starts, &e->in_start_pos,
@@ -428,15 +496,18 @@ extern "C" int32_t b2llm_engine_destroy(b2llm_engine* e) {
 
 extern "C" int32_t b2llm_engine_kv_bytes_per_token(const b2llm_engine* e, uint64_t* cache_bytes, uint64_t* scale_bytes) {
     B2_REQUIRE(e && cache_bytes && scale_bytes, B2LLM_ERR_INVALID_VALUE, "null argument");
-    *cache_bytes = (uint64_t)e->d.num_layers * 2 * e->nkv * e->D;
-    *scale_bytes = (uint64_t)e->d.num_layers * 2 * e->nkv * e->D / e->d.cache_quant_group * 2;
+    // resource_manager.cc:381-388: sizeof(int8 | fp16) per cached element; scale bytes only when cache_quant_bit > 0
+    const bool kv16 = e->d.cache_quant_bit == 0;
+    *cache_bytes = (uint64_t)e->d.num_layers * 2 * e->nkv * e->D * (kv16 ? 2 : 1);
+    *scale_bytes = kv16 ? 0 : (uint64_t)e->d.num_layers * 2 * e->nkv * e->D / e->d.cache_quant_group * 2;
     return B2LLM_OK;
 }
 
 extern "C" int32_t b2llm_engine_bind_kv(b2llm_engine* e, void* kv_cache_device, void* kv_scale_device,
                                         uint64_t kv_cache_max_tokens) {
-    B2_REQUIRE(e && kv_cache_device && kv_scale_device && kv_cache_max_tokens > 0, B2LLM_ERR_INVALID_VALUE,
-               "bind_kv: null / empty KV memory");
+    B2_REQUIRE(e && kv_cache_device && kv_cache_max_tokens > 0, B2LLM_ERR_INVALID_VALUE, "bind_kv: null / empty KV memory");
+    B2_REQUIRE(kv_scale_device || e->d.cache_quant_bit == 0, B2LLM_ERR_INVALID_VALUE,
+               "bind_kv: the int8 cache needs its scale memory (runtime input 10, llm_engine.h:134-136)");
     e->kv_cache = kv_cache_device;
     e->kv_scale = kv_scale_device;
     e->geom.max_tokens = kv_cache_max_tokens;
@@ -713,7 +784,8 @@ extern "C" int32_t b2llm_engine_run(b2llm_engine* e, int32_t cache_prefill, floa
 extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, float** logits_device,
                                         int64_t* logits_stride) {
     B2_REQUIRE(e && st, B2LLM_ERR_INVALID_VALUE, "forward: null argument");
-    B2_REQUIRE(e->kv_cache && e->kv_scale, B2LLM_ERR_INVALID_VALUE, "forward: KV memory not bound (b2llm_engine_bind_kv)");
+    B2_REQUIRE(e->kv_cache && (e->kv_scale || e->d.cache_quant_bit == 0), B2LLM_ERR_INVALID_VALUE,
+               "forward: KV memory not bound (b2llm_engine_bind_kv)");
     const b2llm_model_desc& d = e->d;
     const int64_t T = st->num_tokens, B = st->batch;
     B2_REQUIRE(T >= 0 && T <= e->cap_tokens && B >= 0 && B <= e->cap_batch, B2LLM_ERR_INVALID_VALUE,
@@ -744,23 +816,29 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
     aa.split_k = e->split_k;
     const int64_t decode_tokens = st->decoding_batches;  // one token per decoding sequence, placed first
     const bool tp = e->tp > 1;
-    const __half* pending_skip = nullptr;  // tp > 1: all-reduced projection output not yet added to x
+    const __half* pending_skip = nullptr;  // tp > 1, NCCL path: all-reduced projection output not yet added to x
+    bool fused = tp && e->tp_fused;
+    if (fused && !e->comm_mapped) {
+        if ((rc = map_comm(e))) return rc;
+    }
+    const int join_mode = i8 ? 1 : 2;      // what the fused join leaves for the next block: int8 + scale, or fp16
+    bool have_norm = false;                 // the fused join already wrote norm(x) of the upcoming block into a8 / y16
 
     for (int l = 0; l < d.num_layers; ++l) {
         Layer& L = e->layers[l];
         // ---- attention block
-        const void* lin_in;
-        if (i8) {
-            rc = launch_rmsnorm_quant(s, x, pending_skip, L.attn_norm.as<__half>(), d.norm_eps, T, h, e->a8.as<int8_t>(),
-                                      e->a_s.as<float>(), nullptr);
-            lin_in = e->a8.p;
-        } else {
-            rc = launch_rmsnorm_quant(s, x, pending_skip, L.attn_norm.as<__half>(), d.norm_eps, T, h, nullptr, nullptr,
-                                      e->y16.as<__half>());
-            lin_in = e->y16.p;
+        const void* lin_in = i8 ? e->a8.p : e->y16.p;
+        if (!have_norm) {
+            if (i8)
+                rc = launch_rmsnorm_quant(s, x, pending_skip, L.attn_norm.as<__half>(), d.norm_eps, T, h, e->a8.as<int8_t>(),
+                                          e->a_s.as<float>(), nullptr);
+            else
+                rc = launch_rmsnorm_quant(s, x, pending_skip, L.attn_norm.as<__half>(), d.norm_eps, T, h, nullptr, nullptr,
+                                          e->y16.as<__half>());
+            if (rc) return rc;
         }
         pending_skip = nullptr;
-        if (rc) return rc;
+        have_norm = false;
         if ((rc = gemm(e, lin_in, e->a_s.as<float>(), L.qkv, T, EPI_F16, e->qkv.p, e->nqkv))) return rc;
         if ((rc = launch_rope_kv_append(s, e->qkv.as<__half>(), st, e->nq, e->geom, l, e->rope_cos.as<float>(),
                                         e->rope_sin.as<float>(), (int8_t*)e->kv_cache, (__half*)e->kv_scale)))
@@ -785,21 +863,27 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
             if ((rc = gemm(e, lin_in, e->a_s.as<float>(), L.o, T, EPI_RESIDUAL, x, h))) return rc;
         } else {
             if ((rc = gemm(e, lin_in, e->a_s.as<float>(), L.o, T, EPI_F16, e->tmp.p, h))) return rc;
-            if ((rc = allreduce_half(e, e->tmp.as<__half>(), (size_t)T * h))) return rc;
-            pending_skip = e->tmp.as<__half>();
+            if (fused) {  // all-reduce + residual + ffn RMSNorm + quant, one kernel over peer memory
+                if ((rc = tp_join(e, join_mode, false, L.ffn_norm.as<__half>(), T))) return rc;
+                have_norm = true;
+            } else {
+                if ((rc = allreduce_half(e, e->tmp.as<__half>(), (size_t)T * h))) return rc;
+                pending_skip = e->tmp.as<__half>();
+            }
         }
         // ---- feed-forward block
-        if (i8) {
-            rc = launch_rmsnorm_quant(s, x, pending_skip, L.ffn_norm.as<__half>(), d.norm_eps, T, h, e->a8.as<int8_t>(),
-                                      e->a_s.as<float>(), nullptr);
-            lin_in = e->a8.p;
-        } else {
-            rc = launch_rmsnorm_quant(s, x, pending_skip, L.ffn_norm.as<__half>(), d.norm_eps, T, h, nullptr, nullptr,
-                                      e->y16.as<__half>());
-            lin_in = e->y16.p;
+        lin_in = i8 ? e->a8.p : e->y16.p;
+        if (!have_norm) {
+            if (i8)
+                rc = launch_rmsnorm_quant(s, x, pending_skip, L.ffn_norm.as<__half>(), d.norm_eps, T, h, e->a8.as<int8_t>(),
+                                          e->a_s.as<float>(), nullptr);
+            else
+                rc = launch_rmsnorm_quant(s, x, pending_skip, L.ffn_norm.as<__half>(), d.norm_eps, T, h, nullptr, nullptr,
+                                          e->y16.as<__half>());
+            if (rc) return rc;
         }
         pending_skip = nullptr;
-        if (rc) return rc;
+        have_norm = false;
         if ((rc = gemm(e, lin_in, e->a_s.as<float>(), L.gate_up, T, EPI_SWIGLU, e->act.p, e->inter))) return rc;
         if (i8) {
             if ((rc = launch_quant_rows(s, e->act.as<__half>(), T, e->inter, e->b8.as<int8_t>(), e->b_s.as<float>()))) return rc;
@@ -811,8 +895,17 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
             if ((rc = gemm(e, lin_in, e->b_s.as<float>(), L.down, T, EPI_RESIDUAL, x, h))) return rc;
         } else {
             if ((rc = gemm(e, lin_in, e->b_s.as<float>(), L.down, T, EPI_F16, e->tmp.p, h))) return rc;
-            if ((rc = allreduce_half(e, e->tmp.as<__half>(), (size_t)T * h))) return rc;
-            pending_skip = e->tmp.as<__half>();
+            if (fused) {
+                // ... + the NEXT layer's attention RMSNorm + quant; the last join of the step only completes the residual
+                // stream and gives every rank all of its rows (the lm head needs the last token of every sequence)
+                const bool last = l + 1 == d.num_layers;
+                if ((rc = tp_join(e, last ? 0 : join_mode, last, last ? nullptr : e->layers[l + 1].attn_norm.as<__half>(), T)))
+                    return rc;
+                have_norm = !last;
+            } else {
+                if ((rc = allreduce_half(e, e->tmp.as<__half>(), (size_t)T * h))) return rc;
+                pending_skip = e->tmp.as<__half>();
+            }
         }
     }
     if (pending_skip) {  // fold the last all-reduced output into x (norm output unused)
@@ -945,8 +1038,8 @@ extern "C" int32_t b2llm_op_gemm_f16(void* stream, const void* a_fp16, const voi
 extern "C" int32_t b2llm_op_rope_kv_append(void* stream, void* qkv_fp16, const b2llm_step* step, int32_t num_heads,
                                            const b2llm_kv_geom* geom, int32_t layer, const float* rope_cos,
                                            const float* rope_sin, void* kv_cache, void* kv_scale) {
-    B2_REQUIRE(qkv_fp16 && step && geom && rope_cos && rope_sin && kv_cache && kv_scale, B2LLM_ERR_INVALID_VALUE,
-               "rope_kv_append: null pointer");
+    B2_REQUIRE(qkv_fp16 && step && geom && rope_cos && rope_sin && kv_cache && (kv_scale || geom->quant_group == 1),
+               B2LLM_ERR_INVALID_VALUE, "rope_kv_append: null pointer");
     return launch_rope_kv_append((cudaStream_t)stream, (__half*)qkv_fp16, step, num_heads, *geom, layer, rope_cos, rope_sin,
                                  (int8_t*)kv_cache, (__half*)kv_scale);
 }
@@ -958,7 +1051,8 @@ extern "C" int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_hea
 extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const b2llm_step* step, int32_t num_heads,
                                       const b2llm_kv_geom* geom, int32_t layer, const void* kv_cache, const void* kv_scale,
                                       void* workspace, void* out_fp16, int32_t impl) {
-    B2_REQUIRE(qkv_fp16 && step && geom && kv_cache && kv_scale && out_fp16, B2LLM_ERR_INVALID_VALUE, "attention: null pointer");
+    B2_REQUIRE(qkv_fp16 && step && geom && kv_cache && (kv_scale || geom->quant_group == 1) && out_fp16, B2LLM_ERR_INVALID_VALUE,
+               "attention: null pointer");
     AttnArgs aa{};
     aa.qkv = (const __half*)qkv_fp16;
     aa.step = step;

@@ -278,7 +278,8 @@ class CudaResourceManager:
                 kv_cache_max_tokens = int(t.item())
         self.kv_cache_max_tokens = int(kv_cache_max_tokens)
         self.kv_cache_mem = torch.empty(self.kv_cache_max_tokens * cb, dtype=torch.int8, device="cuda")
-        self.kv_scale_mem = torch.empty(self.kv_cache_max_tokens * sb // 2, dtype=torch.float16, device="cuda")
+        # cache_quant_bit 0: fp16 cache, no scale memory (resource_manager.cc:353-361 allocates it only when sb > 0)
+        self.kv_scale_mem = torch.empty(self.kv_cache_max_tokens * sb // 2, dtype=torch.float16, device="cuda") if sb else None
         return self.lib.b2llm_engine_bind_kv(eng, _ptr(self.kv_cache_mem), _ptr(self.kv_scale_mem),
                                              self.kv_cache_max_tokens)
 

@@ -491,7 +491,8 @@ public:
                             {"kv_starts", DATATYPE_INT64},      {"cache_indices", DATATYPE_INT64}, {"decoding_batches", DATATYPE_INT64},
                             {"start_pos", DATATYPE_INT64},      {"max_seq_len", DATATYPE_INT64},  {"max_kv_len", DATATYPE_INT64},
                             {"kv_cache", DATATYPE_INT8},        {"kv_scale", DATATYPE_FLOAT16}};
-        for (int i = 0; i < IN_COUNT; ++i) inputs_.emplace_back(new B200Tensor(defs[i].name, defs[i].dt));
+        for (int i = 0; i < IN_COUNT; ++i)
+            inputs_.emplace_back(new B200Tensor(defs[i].name, (i == IN_KV_CACHE && slice_.d.cache_quant_bit == 0) ? DATATYPE_FLOAT16 : defs[i].dt));
         for (int i : {IN_DECODING_BATCHES, IN_MAX_SEQ_LEN, IN_MAX_KV_LEN}) inputs_[i]->GetShape()->ReshapeAsScalar();
         logits_.reset(new B200Tensor("logits", DATATYPE_FLOAT32));
         logits_->GetShape()->Reshape({0, slice_.d.vocab_size});
@@ -539,7 +540,8 @@ public:
                 return RC_INVALID_VALUE;
             }
         }
-        if (!kv->GetBufferPtr() || !ks->GetBufferPtr()) {
+        // cache_quant_bit 0: fp16 cache, input 10 (kv_scale) does not exist (llm_engine.h:134-136, 145-147)
+        if (!kv->GetBufferPtr() || (d.cache_quant_bit > 0 && !ks->GetBufferPtr())) {
             LOG(ERROR) << "Run: kv_cache / kv_scale buffers have not been bound (Tensor::SetBufferPtr)";
             return RC_INVALID_VALUE;
         }

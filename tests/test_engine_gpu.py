@@ -28,6 +28,9 @@ from helpers import random_pages
 
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3
+# every logits row compared in this module: quant method -> [rows, rows beyond the STRICT 1e-3 bar, worst rel err];
+# reported and bounded by test_zz_rows_beyond_strict_tolerance ("how many rows needed the widened bar")
+ROW_STATS = {}
 
 
 def _model_input_from_step(step: ref.Step, desc) -> ModelInput:
@@ -63,6 +66,10 @@ def _check_step(engine, oracle, oracle_nudged, desc, step, req_changed, tag):
     rel_rows = (np.abs(got_logits - exp_logits) / scale).max(axis=1)
     floor = float((np.abs(nudged - exp_logits) / scale).max())
     tol = max(LOGIT_TOL, 1.5 * floor)
+    st = ROW_STATS.setdefault(int(desc.quant_method), [0, 0, 0.0])
+    st[0] += B
+    st[1] += int((rel_rows > LOGIT_TOL).sum())
+    st[2] = max(st[2], float(rel_rows.max()))
     assert rel_rows.max() <= tol, f"{tag}: logits rel err {rel_rows.max()} > {tol} (oracle 1-ulp self-response {floor})"
     exp_tok, exp_lp = sampler_ref.sample_topk_topp(exp_logits, None, None, None, desc.vocab_size, 1, 0.0)
     for b in range(B):
@@ -130,6 +137,30 @@ def test_generation_gqa_and_loaded_weights():
     # 8 q heads over 2 kv heads; weights go through b2llm_engine_load_weight instead of random_init
     desc = ModelDesc(1024, 512, 2, 8, 2, 512, cache_layout=3, cache_mode=1, page_size=16, max_position=256)
     _run_generation(desc, [4, 12, 7], 4, seed=3, kv_tokens=512, use_loaded_weights=True)
+
+
+@pytest.mark.parametrize("quant", [1, 0])
+@pytest.mark.parametrize("layout,mode,page", [(3, 1, 16), (0, 0, 16), (1, 1, 8), (2, 1, 64)])
+def test_generation_fp16_cache(layout, mode, page, quant):
+    """cache_quant_bit 0 / cache_quant_group 1: the fp16 KV cache the reference accepts beside int8 group 8
+    (llm_generator.cc:131-136; no scale tensor, resource_manager.cc:381-388), W8A8 and fp16 weights, GQA, all layouts"""
+    desc = ModelDesc(512, 1024, 2, 4, 2, 1024, cache_layout=layout, cache_mode=mode, page_size=page, quant_method=quant,
+                     max_position=256, cache_quant_bit=0, cache_quant_group=1)
+    mism, rels = _run_generation(desc, [5, 17, 1, 33], 5, seed=20 + layout, kv_tokens=1024)
+    assert mism == 0, f"{mism} greedy tokens differ, worst logits rel err {rels.max()}"
+
+
+def test_kv_budget_fp16_cache():
+    """KV budget of the fp16 cache: cb doubles, sb = 0 (resource_manager.cc:329-342, 381-388)"""
+    import ctypes as C
+    desc = ModelDesc(512, 1024, 2, 4, 2, 1024, max_position=64, cache_quant_bit=0, cache_quant_group=1)
+    res = CudaResourceManager()
+    assert res.Init(desc, 0.9, 4, 32, kv_cache_max_tokens=64) == RC_SUCCESS
+    cb, sb = C.c_uint64(), C.c_uint64()
+    res.lib.b2llm_engine_kv_bytes_per_token(res.engine, C.byref(cb), C.byref(sb))
+    assert (cb.value, sb.value) == desc.kv_bytes_per_token() == (2 * 2 * 2 * 128 * 2, 0)
+    assert res.kv_scale_mem is None and res.kv_cache_mem.numel() == 64 * cb.value
+    res.close()
 
 
 def test_generation_fp16_weights():
@@ -255,3 +286,25 @@ def test_full_size_paging_invariance_and_split_modes():
     rel = np.abs(l2 - la).max(axis=1) / np.abs(la).max(axis=1)
     assert rel.max() <= 0.1 and (t2 == ta).mean() >= 0.95, (rel.max(), (t2 == ta).mean())
     res.close()
+
+
+def test_zz_rows_beyond_strict_tolerance():
+    """Runs last in this module.  The per-row bar above is max(1e-3, 1.5 x the oracle's own response to a one-ulp
+    nudge); this reports how many of the compared logits rows actually needed more than the STRICT 1e-3 and bounds it.
+    Measured on B200 (round 2 run 3, profiles/r2_parity_rows_run3.json): W8A8 9 of 163 rows (5.5 %), fp16 weights 3 of 92
+    (3.3 %), W4A16 0 of 22 -- and no row anywhere beyond 2.0e-3.  So: at most 10 % of the rows of any mode between 1e-3 and
+    the hard ceiling of 3e-3 of the row's max |logit|."""
+    import json
+    import os
+    names = {0: "none (fp16 weights)", 1: "online_i8i8 (W8A8)", 2: "w4a16"}
+    report = {names[q]: {"rows": v[0], "rows_beyond_1e-3": v[1], "fraction": v[1] / max(1, v[0]), "worst_rel_err": v[2]}
+              for q, v in sorted(ROW_STATS.items())}
+    print("\nlogits rows vs oracle:", json.dumps(report, indent=1))
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/parity_rows.json", "w") as f:
+            json.dump(report, f, indent=1)
+    if not ROW_STATS:
+        pytest.skip("no generation test ran before this one")
+    for q, v in ROW_STATS.items():
+        assert v[1] <= 0.10 * v[0], f"{names[q]}: {v[1]} of {v[0]} rows beyond the strict 1e-3 (bound 10 %)"
+        assert v[2] <= 3e-3, f"{names[q]}: worst logits row {v[2]} beyond the hard ceiling 3e-3"

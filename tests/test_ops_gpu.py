@@ -254,9 +254,10 @@ def test_gemm_f16_logits(lib, impl, M, N, K):
 
 
 # ------------------------------------------------------------------ rope + KV append
-def _mk_desc(layout, mode, nq=4, nkv=2, D=128, layers=2, page=16):
+def _mk_desc(layout, mode, nq=4, nkv=2, D=128, layers=2, page=16, kvbit=8):
+    """kvbit 8: int8 cache, fp16 scale per 8 elements; kvbit 0: fp16 cache, no scale tensor (llm_generator.cc:131-136)"""
     return ModelDesc(nq * D, 256, layers, nq, nkv, 512, cache_layout=layout, cache_mode=mode, page_size=page,
-                     max_position=512)
+                     max_position=512, cache_quant_bit=kvbit, cache_quant_group=8 if kvbit else 1)
 
 
 def _ragged_step(desc, rng, seqlens, start_pos, decoding, T_cache):
@@ -271,10 +272,11 @@ def _ragged_step(desc, rng, seqlens, start_pos, decoding, T_cache):
     return ref.build_step(desc, toks, start_pos, decoding, cache_indices=[i * stride for i in range(B)])
 
 
+@pytest.mark.parametrize("kvbit", [8, 0])
 @pytest.mark.parametrize("layout", [0, 1, 2, 3])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_rope_kv_append_bit_exact(lib, layout, mode):
-    desc = _mk_desc(layout, mode)
+def test_rope_kv_append_bit_exact(lib, layout, mode, kvbit):
+    desc = _mk_desc(layout, mode, kvbit=kvbit)
     rng = np.random.default_rng(layout * 2 + mode)
     T_cache = 512
     step = _ragged_step(desc, rng, [1, 1, 7, 20], [30, 5, 0, 3], 2, T_cache)
@@ -308,13 +310,12 @@ def test_rope_kv_append_bit_exact(lib, layout, mode):
     q = ref.apply_rope(qkv[:, :nq * D].reshape(T, nq, D), pos, cos, sin)
     k = ref.apply_rope(qkv[:, nq * D:(nq + nkv) * D].reshape(T, nkv, D), pos, cos, sin)
     v = qkv[:, (nq + nkv) * D:].reshape(T, nkv, D)
-    k8, ks = ref.kv_quant(k); v8, vs = ref.kv_quant(v)
-    cache.write(layer, slots, k8, ks, v8, vs)
+    cache.append(layer, slots, k, v)
     ec, es = cache.export()
     got = qd.cpu().numpy()
     assert np.array_equal(got[:, :nq * D].view(np.uint16), q.reshape(T, -1).view(np.uint16))
     assert np.array_equal(got[:, nq * D:(nq + nkv) * D].view(np.uint16), k.reshape(T, -1).view(np.uint16))
-    assert np.array_equal(cd.cpu().numpy(), ec)
+    assert np.array_equal(cd.cpu().numpy().view(np.uint8), ec.view(np.uint8))   # int8 values, or the fp16 rows bit for bit
     assert np.array_equal(sd.cpu().numpy().view(np.uint16), es.view(np.uint16))
 
 
@@ -333,13 +334,13 @@ def _attention_case(lib, desc, seqlens, start_pos, decoding, impl, T_cache=2048,
             sl = step.slots(desc, b, np.arange(sp))
             kh = rng.standard_normal((sp, nkv, D)).astype(np.float16)
             vh = rng.standard_normal((sp, nkv, D)).astype(np.float16)
-            cache.write(layer, sl, *ref.kv_quant(kh), *ref.kv_quant(vh))
+            cache.append(layer, sl, kh, vh)
     qkv = rng.standard_normal((T, (nq + 2 * nkv) * D)).astype(np.float16)
     seqlens_a = np.diff(step.seq_starts)
     slots = np.concatenate([step.slots(desc, b, step.start_pos[b] + np.arange(seqlens_a[b])) for b in range(step.batch)])
     k = qkv[:, nq * D:(nq + nkv) * D].reshape(T, nkv, D)
     v = qkv[:, (nq + nkv) * D:].reshape(T, nkv, D)
-    cache.write(layer, slots, *ref.kv_quant(k), *ref.kv_quant(v))
+    cache.append(layer, slots, k, v)
     q = qkv[:, :nq * D].reshape(T, nq, D)
     exp = np.empty((T, nq, D), dtype=np.float32)
     for b in range(step.batch):
@@ -351,8 +352,8 @@ def _attention_case(lib, desc, seqlens, start_pos, decoding, impl, T_cache=2048,
             Kf, Vf = k[t0:t1].astype(np.float32), v[t0:t1].astype(np.float32)
             if sp:
                 sl = step.slots(desc, b, np.arange(sp))
-                Kf = np.concatenate([ref.kv_dequant(*cache.read(layer, 0, sl)), Kf])
-                Vf = np.concatenate([ref.kv_dequant(*cache.read(layer, 1, sl)), Vf])
+                Kf = np.concatenate([cache.read_values(layer, 0, sl), Kf])
+                Vf = np.concatenate([cache.read_values(layer, 1, sl), Vf])
             exp[t0:t1] = ref._attend(q[t0:t1].astype(np.float32), Kf, Vf, sp + np.arange(n))
     c_np, s_np = cache.export()
     keep = []
@@ -411,6 +412,26 @@ def test_attention_long_ragged_batch(lib):
     rng = np.random.default_rng(0)
     lens = [int(x) for x in rng.integers(1, 400, 48)]
     _attention_case(lib, desc, [1] * 48, lens, 48, 2, T_cache=48 * 416, seed=5)
+
+
+@pytest.mark.parametrize("impl", [1, 2, 5, 7])  # simple kernel; tensor-core kernel: merged (default) / slim TMA loaders, cp.async
+@pytest.mark.parametrize("layout,mode,page", [(3, 1, 16), (2, 0, 16), (1, 1, 64), (0, 0, 16), (3, 1, 8)])
+def test_attention_fp16_cache(lib, impl, layout, mode, page):
+    """cache_quant_bit 0 / group 1 (llm_generator.cc:131-136): K and V are cached as fp16, no scale tensor.  Decode (MHA,
+    GQA 8 with split-KV + merge, ragged batch) and prefill with a cached prefix, all layouts; page size 8 forces the
+    cp.async loader (units are not 16 contiguous slots)"""
+    if impl == 7 and page != 8:
+        pytest.skip("impl 7 = default dispatch on a page size the TMA loaders cannot serve")
+    if impl != 7 and page == 8 and impl != 1:
+        pytest.skip("TMA loaders need page_size % 16 == 0")
+    impl = 2 if impl == 7 else impl
+    kw = dict(page=page, kvbit=0)
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, **kw), [1] * 5, [0, 15, 16, 100, 333], 5, impl, seed=layout)
+    _attention_case(lib, _mk_desc(layout, mode, nq=8, nkv=1, **kw), [1, 1], [1500, 700], 2, impl, T_cache=4096, seed=3)
+    rng = np.random.default_rng(0)
+    lens = [int(x) for x in rng.integers(1, 400, 48)]
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, **kw), [1] * 48, lens, 48, impl, T_cache=48 * 512, seed=5)
+    _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=2, **kw), [1, 1, 9, 70], [64, 7, 0, 32], 2, impl, seed=11)
 
 
 @pytest.mark.parametrize("impl", [4, 5])  # 4: dividing loader (default until run 17), 5: slim loader (default since)

@@ -194,3 +194,29 @@ def test_penalty_reference_semantics():
     assert out[0, 10] == pytest.approx(0.7, abs=1e-6)
     assert out[0, 0] == pytest.approx(-3.0)                      # unseen: only the temperature
     assert out[1, 7] == pytest.approx(1.0 / 1.5, abs=1e-6)
+
+
+def test_fp16_cache_decode_equals_prefill_of_the_longer_prompt():
+    """cache_quant_bit 0 / group 1 (llm_generator.cc:131-136): the cache holds the rotated K and V as fp16, exactly the
+    values prefill attention uses for fresh tokens -- so decoding token n after a prefill of n tokens must give the
+    logits of a prefill over n + 1 tokens (a property the int8 cache does not have: it re-reads quantised values)."""
+    desc = ModelDesc(256, 512, 2, 4, 2, 512, cache_layout=2, cache_mode=1, page_size=8, quant_method=0, max_position=64,
+                     cache_quant_bit=0, cache_quant_group=1)
+    assert desc.kv_bytes_per_token() == (2 * 2 * 2 * 64 * 2, 0)
+    w = SynthWeights(desc, 7)
+    rng = np.random.default_rng(3)
+    toks = list(map(int, rng.integers(0, desc.vocab_size, 12)))
+    pages = [[16, 0, 8]]
+    a = ref.LlamaOracle(desc, w, 32)
+    a.forward(ref.build_step(desc, [toks[:11]], [0], 0, page_tables=pages))
+    dec = a.forward(ref.build_step(desc, [toks[11:]], [11], 1, page_tables=pages))
+    b = ref.LlamaOracle(desc, w, 32)
+    full = b.forward(ref.build_step(desc, [toks], [0], 0, page_tables=pages))
+    assert a.cache.cache.dtype == np.float16 and a.cache.scale.size == 0
+    assert np.array_equal(a.cache.cache, b.cache.cache)
+    np.testing.assert_allclose(dec, full, rtol=0, atol=2e-3 * np.abs(full).max())
+    # and the layouts round-trip through export / load
+    c, s = a.cache.export()
+    k = ref.KVCache(desc, 32)
+    k.load(c, s)
+    assert np.array_equal(k.cache, a.cache.cache)
