@@ -418,8 +418,9 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
         torch.cuda.synchronize()
 
     out = {"tensor_parallel_size": world,
-           "collectives": "ncclAllReduce(fp16 sum, [tokens, hidden]) after o_proj and after down_proj of every layer on the "
-                          "rank's stream + one ncclAllGather(fp32) of the vocab-parallel logits per step",
+           "collectives": "after o_proj and after down_proj of every layer (the two residual join points): one fused kernel over "
+                          "NVLink peer memory = all-reduce of the fp16 partials + residual add + RMSNorm + int8 quant (ncclAllReduce + "
+                          "separate kernels with B2LLM_TP_JOIN=nccl); + one ncclAllGather(fp32) of the vocab-parallel logits per step",
            "parity_gate": [], "runs": []}
     quants = [1] + ([2] if world == 8 else [])
     for q in quants:
@@ -449,7 +450,10 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
             else:
                 for _ in range(args.warmup):
                     run.device_step()
+                js = (C.c_double * 4)()
+                run.lib.b2llm_engine_tp_join_stats(run.res.engine, js)   # reset: count the timed loop only
                 ms = run.time_device(args.steps, barrier)
+                run.lib.b2llm_engine_tp_join_stats(run.res.engine, js)
                 cls_ms, cls_n = run.profile_classes(min(args.steps, 5))
                 ms_e2e = run.time_e2e(min(args.steps, 10), barrier) / min(args.steps, 10) * args.steps
                 t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -469,6 +473,14 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
                                          "frac_of_hbm_roofline": step_bytes / (hbm_peak * 1e9) * 1e3 / ms},
                     "attention_GBps_per_gpu": attn_bytes / (cls_ms[0] / max(1.0, cls_n[0]) * 1e-3) / 1e9 if cls_ms[0] > 0 else None,
                 })
+                if js[0] > 0:  # the fused join's own phase clocks (rank 0), microseconds per call in the timed loop
+                    entry["fused_join_us_per_call"] = {"calls_per_step": js[0] / args.steps,
+                                                       "waiting_for_peers_partials (rank skew)": js[1] / js[0] * 1e-3,
+                                                       "reduce_norm_quant_deliver": js[2] / js[0] * 1e-3,
+                                                       "waiting_for_peers_rows": js[3] / js[0] * 1e-3}
+                    entry["exchange"] = "fused all-reduce + residual + RMSNorm + quant kernel over NVLink peer memory (csrc/tp_join.cu)"
+                else:
+                    entry["exchange"] = "ncclAllReduce + separate residual / RMSNorm / quant kernels (B2LLM_TP_JOIN=nccl)"
         except Exception as ex:
             entry["error"] = repr(ex)[:400]
         finally:
@@ -478,7 +490,7 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
     ok_runs = [r for r in out["runs"] if "ms_per_step" in r]
     if ok_runs:
         worst = max(ok_runs, key=lambda r: r["collective_share_of_step"])
-        out["limiting_collective"] = (f"ncclAllReduce x {2 * worst['layers']} per step: {worst['allreduce_ms_per_step']:.2f} ms = "
+        out["limiting_collective"] = (f"residual join x {2 * worst['layers']} per step (+ logits all-gather): {worst['allreduce_ms_per_step']:.2f} ms = "
                                       f"{100 * worst['collective_share_of_step']:.0f} % of the {worst['model']} TP={world} step")
     nccl.destroy_comm(comm)
     return out

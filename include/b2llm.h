@@ -195,11 +195,17 @@ B2LLM_API int32_t b2llm_engine_staged_inputs(b2llm_engine* e, const int64_t** to
 B2LLM_API int64_t b2llm_engine_last_launch_count(const b2llm_engine* e);
 /* per-kernel-class device timing with CUDA events on the engine stream (bench.py's roofline leg).
  * classes: 0 attention (decode attention kernel [+ split merge, + prefill attention]), 1 the layer
- * GEMMs, 2 lm_head.  profile(e, 1) starts recording; profile_read sums the spans recorded since,
+ * GEMMs, 2 lm_head, 3 tensor-parallel exchanges (the fused residual joins or ncclAllReduce, + the logits
+ * all-gather).  profile(e, 1) starts recording; profile_read sums the spans recorded since,
  * synchronises the stream, and resets. */
 B2LLM_API int32_t b2llm_engine_profile(b2llm_engine* e, int32_t enable);
 B2LLM_API int32_t b2llm_engine_profile_read(b2llm_engine* e, double* ms_by_class, int64_t* count_by_class,
                                             int32_t num_classes);
+/* tensor parallelism: phase clocks of the fused residual-join kernel (csrc/tp_join.cu) accumulated since the last
+ * call, read from the device and reset: out4 = { calls, ns waiting for the peers' partial sums (rank skew), ns
+ * reducing / normalising / delivering this rank's rows, ns waiting for the peers' rows to land }.  Zeros when the
+ * engine is not tensor parallel or uses the ncclAllReduce path (B2LLM_TP_JOIN=nccl). */
+B2LLM_API int32_t b2llm_engine_tp_join_stats(b2llm_engine* e, double* out4);
 /* debugging / parity: copy an intermediate of the last forward to the host.
  * what: 0 residual stream fp16 [num_tokens, hidden] after the last layer; 1 qkv fp16 (last layer, after
  * rope); 2 attention output fp16 (last layer); 3 logits fp32 [batch, vocab] */

@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     constexpr bool TMA = LOADER != 0, SLIM = LOADER >= 2, MERGED = LOADER == 3;
     constexpr int STG = KV16 ? STAGE16 : STAGE;  // bytes per ring stage
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int split = blockIdx.x, b = blockIdx.z;
@@ -396,15 +397,6 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bars = smem_base + WARPS * NSTAGE * STG;
 
-    const int kv_len = (int)(p.start_pos[b] + 1);
-    const int units_total = (kv_len + UNIT - 1) / UNIT;
-    const int units_per_split = (units_total + p.nsplit - 1) / p.nsplit;
-    const int u0 = split * units_per_split;
-    const int u1 = min(units_total, u0 + units_per_split);
-
-    const int heads = p.nq + 2 * p.nkv;
-    const int64_t tok = b;  // decode sequences come first, one token each (seq_starts[b] == b)
-
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             for (int i = 0; i < WARPS * NSTAGE; ++i) mbar_init(bars + 8u * i, 1);
@@ -414,6 +406,16 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
         }
         __syncthreads();
     }
+    pdl_wait();  // everything above is local to the CTA; q, start_pos and this step's K / V rows come from earlier kernels
+
+    const int kv_len = (int)(p.start_pos[b] + 1);
+    const int units_total = (kv_len + UNIT - 1) / UNIT;
+    const int units_per_split = (units_total + p.nsplit - 1) / p.nsplit;
+    const int u0 = split * units_per_split;
+    const int u1 = min(units_total, u0 + units_per_split);
+
+    const int heads = p.nq + 2 * p.nkv;
+    const int64_t tok = b;  // decode sequences come first, one token each (seq_starts[b] == b)
 
     // ---- Q^T fragments (B operand, column n = g is q head hq0 + g; columns >= nrow are zero).  k-slot
     // order follows the K byte order: step j, lane t covers d = 32 t + 4 j + {0,2} (b0) and {1,3} (b1)
@@ -747,6 +749,8 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
 // merge split partials: one warp per (sequence, q head)
 __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict__ ws, int nq, int nsplit, int64_t rows,
                                                         __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= rows) return;
@@ -962,11 +966,11 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
     const int gq = p.nq / p.nkv;
     const int chunks = (gq + G - 1) / G;
     dim3 grid(p.nsplit, p.nkv * chunks, p.decoding_batches);
-    kern<<<grid, WARPS * 32, smem_bytes, s>>>(p, maps.kv, maps.sc, tc);
+    launch_kernel(kern, grid, dim3(WARPS * 32), smem_bytes, s, p, maps.kv, maps.sc, tc);
     B2_LAUNCH_CHECK();
     if (p.nsplit > 1) {
         const int64_t rows = (int64_t)p.decoding_batches * p.nq;
-        attn_merge_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(p.ws, p.nq, p.nsplit, rows, p.out);
+        launch_kernel(attn_merge_kernel, dim3((unsigned)((rows + 3) / 4)), dim3(128), 0, s, (const float*)p.ws, p.nq, p.nsplit, rows, p.out);
         B2_LAUNCH_CHECK();
     }
     return B2LLM_OK;

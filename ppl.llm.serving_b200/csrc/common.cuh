@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b2llm.h"
@@ -60,6 +61,31 @@ extern thread_local int64_t g_launch_count;  // kernels launched by this thread 
     } while (0)
 
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may be scheduled
+// while its predecessor in the stream is still draining, runs its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch, index arithmetic) and blocks in griddepcontrol.wait until the predecessor has COMPLETED and its writes are
+// visible -- the ~325 launch / drain gaps of a decode step overlap instead of adding up.  Rules every kernel follows:
+//   * pdl_trigger() first (dependents may be scheduled once every CTA of this grid has started);
+//   * no global-memory access that depends on an earlier kernel before pdl_wait().
+// B2LLM_PDL=0 launches everything fully serialised (the instructions are no-ops then).
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------ KV addressing
 // Element strides of the int8 cache for the reference's four layouts (llm_engine.cc:118-169).
 // The fp16 scale tensor has the same strides divided by quant_group.
@@ -81,6 +107,9 @@ inline KvStrides kv_strides(const b2llm_kv_geom& g) {
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

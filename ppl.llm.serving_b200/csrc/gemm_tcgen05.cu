@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int nk = (Kb + BKB - 1) / BKB;  // a partial last k-block reads zeros beyond K (TMA out-of-bounds fill) in A and W
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -202,16 +203,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
             tma_prefetch_desc(&map_w);
+            // programmatic dependent launch: the WEIGHT tiles of the first ring fill depend on nothing an earlier kernel
+            // of the step wrote -- they are requested before griddepcontrol.wait, so their HBM latency hides behind the
+            // predecessor's tail.  The activation tiles (and everything else) come after the wait.
+            const int pre = blockIdx.x < num_tiles ? (nk < C::STAGES ? nk : C::STAGES) : 0;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(full_bar(kb), C::STAGE_BYTES);
+                tma_load_2d(smem_base + kb * C::STAGE_BYTES + C::A_BYTES, &map_w, full_bar(kb), kb * BKB, (blockIdx.x / num_m) * BN);
+            }
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
+            int done = 0;  // k-blocks issued so far: the first `pre` already have their barrier armed and weights in flight
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+                for (int kb = 0; kb < nk; ++kb, ++done) {
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    if (done >= pre) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        tma_load_2d(sb, &map_w, full_bar(stage), kb * BKB, n_blk * BN);
+                    }
                     tma_load_2d(sa, &map_a, full_bar(stage), kb * BKB, m_blk * BM);
-                    tma_load_2d(sb, &map_w, full_bar(stage), kb * BKB, n_blk * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -246,6 +259,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // epilogue: TMEM lane quarter is fixed by warp id % 4
         const int quarter = warp & 3;
         int it = 0;
+        pdl_wait();  // a_scale, the residual rows and the output buffer belong to earlier kernels
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const int acc = it & 1;
@@ -373,6 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     const int num_m = (M + 2 * BM - 1) / (2 * BM), num_n = N / BN2;
     const int num_tiles = num_m * num_n;
     const int nk = (Kb + BKB - 1) / BKB;  // a partial last k-block reads zeros beyond K (TMA out-of-bounds fill) in A and W
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -399,19 +414,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         if (lane == 0) {
             tma_prefetch_desc(&map_a);
             tma_prefetch_desc(&map_w);
+            // weight halves of the first ring fill go out before griddepcontrol.wait (see gemm_tc_kernel)
+            const int pre = pair < num_tiles ? (nk < C::STAGES ? nk : C::STAGES) : 0;
+            for (int kb = 0; kb < pre; ++kb) {
+                if (rank == 0) mbar_expect_tx(full_bar(kb), 2 * C::STAGE_BYTES);  // both CTAs' bytes
+                tma_load_2d_pair(smem_base + kb * C::STAGE_BYTES + C::A_BYTES, &map_w, mapa_u32(full_bar(kb), 0), kb * BKB,
+                                 (pair / num_m) * BN2 + (int)rank * (BN2 / 2));
+            }
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
+            int done = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
                 const int row_a = m_blk * 2 * BM + (int)rank * BM;
                 const int row_w = n_blk * BN2 + (int)rank * (BN2 / 2);
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+                for (int kb = 0; kb < nk; ++kb, ++done) {
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint32_t fb = mapa_u32(full_bar(stage), 0);
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);  // both CTAs' bytes
+                    if (done >= pre) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);  // both CTAs' bytes
+                        tma_load_2d_pair(sb, &map_w, fb, kb * BKB, row_w);
+                    }
                     tma_load_2d_pair(sa, &map_a, fb, kb * BKB, row_a);
-                    tma_load_2d_pair(sb, &map_w, fb, kb * BKB, row_w);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -446,6 +472,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         const int quarter = warp & 3;
         const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
         int it = 0;
+        pdl_wait();  // a_scale, the residual rows and the output buffer belong to earlier kernels
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const int acc = it & 1;
@@ -537,6 +564,7 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
     const int num_tiles = num_m * num_n;
     const int nk = (2 * K) / BKB;   // k-blocks of 64 elements (128 bytes of fp16)
     const int gpr = K / 128;        // scale groups per output channel
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -558,6 +586,7 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();  // barriers, TMEM and the tensor maps are set up; the activations belong to the predecessor
 
     if (warp == 0) {
         if (lane == 0) {
@@ -725,7 +754,7 @@ int32_t launch(cudaStream_t s, const void* a, const float* a_scale, const void* 
     const int tiles = (int)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int sms = gemm_sm_budget();
     const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
+    launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, s, ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -742,7 +771,7 @@ int32_t launch_pair(cudaStream_t s, const void* a, const float* a_scale, const v
     const int tiles = (int)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
     const int max_pairs = gemm_sm_budget() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    kern<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, s>>>(ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
+    launch_kernel(kern, dim3(2 * pairs), dim3(NUM_THREADS), C::SMEM_BYTES, s, ma, mw, a_scale, w_scale, (int)M, N, Kb, out, ldc);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -801,7 +830,7 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     const int tiles = (int)((M + MT * BM - 1) / (MT * BM)) * (N / W4_BN);
     const int sms = gemm_sm_budget();
     const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, W4_THREADS, C::SMEM_BYTES, s>>>(ma, mw, scale, (int)M, N, K, out, ldc);
+    launch_kernel(kern, dim3(grid), dim3(W4_THREADS), C::SMEM_BYTES, s, ma, mw, scale, (int)M, N, K, out, ldc);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_quant_kernel(__half* __restr
                                                                 __half* __restrict__ y_out) {
     __shared__ float scratch[32];
     __shared__ double dscratch[32];
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = blockIdx.x;
     __half* xr = x + row * hidden;
     const int nvec = hidden >> 3;
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_quant_kernel(__half* __restr
 __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const __half* __restrict__ x, int cols,
                                                              int8_t* __restrict__ q, float* __restrict__ scale) {
     __shared__ float scratch[32];
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = blockIdx.x;
     const __half* xr = x + row * cols;
     const int nvec = cols >> 3;
@@ -191,6 +195,8 @@ __global__ void __launch_bounds__(W == 1 ? 128 : 32 * W)
                          int64_t rows, int cols, int8_t* __restrict__ q, float* __restrict__ scale, __half* __restrict__ y_out) {
     __shared__ float fscratch[W > 1 ? W : 1];
     __shared__ double dscratch[W > 1 ? W : 1];
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = W == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x;
     const int w = W == 1 ? 0 : warp;
@@ -301,7 +307,7 @@ bool launch_row_reg(cudaStream_t s, __half* x, const __half* skip, const __half*
     const int need = (nvec + 32 * W - 1) / (32 * W);
     if (need > 32) return false;  // > 32768 columns: CTA-per-row kernel
     const unsigned blocks = W == 1 ? (unsigned)((rows + 3) / 4) : (unsigned)rows;
-#define B2_ROW_LAUNCH(VV, WW) row_quant_reg_kernel<VV, WW, NORM><<<blocks, WW == 1 ? 128 : 32 * WW, 0, s>>>(x, skip, gamma, eps, rows, cols, q, scale, y)
+#define B2_ROW_LAUNCH(VV, WW) launch_kernel(row_quant_reg_kernel<VV, WW, NORM>, dim3(blocks), dim3(WW == 1 ? 128 : 32 * WW), 0, s, x, skip, gamma, eps, rows, cols, q, scale, y)
 #define B2_ROW_V(WW)                                           \
     if (need <= 4) B2_ROW_LAUNCH(4, WW);                       \
     else if (need <= 8) B2_ROW_LAUNCH(8, WW);                  \
@@ -317,6 +323,8 @@ bool launch_row_reg(cudaStream_t s, __half* x, const __half* skip, const __half*
 // out[i, :] = table[ids[i], :]
 __global__ void embedding_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ table, int hidden, int vocab,
                                  __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = blockIdx.x;
     int64_t id = ids[i];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -327,6 +335,8 @@ __global__ void embedding_kernel(const int64_t* __restrict__ ids, const __half* 
 // out[b, :] = x[seq_starts[b + 1] - 1, :]   (last token of every sequence)
 __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* __restrict__ seq_starts, int hidden,
                                    __half* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t b = blockIdx.x;
     const int64_t t = seq_starts[b + 1] - 1;
     const int nvec = hidden >> 3;
@@ -336,6 +346,8 @@ __global__ void gather_rows_kernel(const __half* __restrict__ x, const int64_t* 
 // all-gathered logits [parts, rows, cols] (rank-major, what ncclAllGather delivers) -> [rows, parts * cols]
 __global__ void __launch_bounds__(256) interleave_blocks_kernel(const float4* __restrict__ src, int parts, int64_t rows, int cols4,
                                                                float4* __restrict__ dst) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t n = (int64_t)parts * rows * cols4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = i % cols4, r = (i / cols4) % rows, p = i / (cols4 * rows);
@@ -365,7 +377,7 @@ int32_t launch_rmsnorm_quant(cudaStream_t s, __half* x, const __half* skip, cons
         B2_LAUNCH_CHECK();
         return B2LLM_OK;
     }
-    rmsnorm_quant_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, skip, gamma, eps, hidden, q, scale, y);
+    launch_kernel(rmsnorm_quant_kernel, dim3((unsigned)rows), dim3(kThreads), 0, s, x, skip, gamma, eps, hidden, q, scale, y);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -377,7 +389,7 @@ int32_t launch_quant_rows(cudaStream_t s, const __half* x, int64_t rows, int col
         B2_LAUNCH_CHECK();
         return B2LLM_OK;
     }
-    quant_rows_kernel<<<(unsigned)rows, kThreads, 0, s>>>(x, cols, q, scale);
+    launch_kernel(quant_rows_kernel, dim3((unsigned)rows), dim3(kThreads), 0, s, x, cols, q, scale);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -385,7 +397,7 @@ int32_t launch_quant_rows(cudaStream_t s, const __half* x, int64_t rows, int col
 int32_t launch_embedding(cudaStream_t s, const int64_t* ids, const __half* table, int64_t n, int hidden, int vocab,
                          __half* out) {
     if (n == 0) return B2LLM_OK;
-    embedding_kernel<<<(unsigned)n, 128, 0, s>>>(ids, table, hidden, vocab, out);
+    launch_kernel(embedding_kernel, dim3((unsigned)n), dim3(128), 0, s, ids, table, hidden, vocab, out);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -393,7 +405,7 @@ int32_t launch_embedding(cudaStream_t s, const int64_t* ids, const __half* table
 int32_t launch_gather_rows(cudaStream_t s, const __half* x, const int64_t* seq_starts, int64_t batch, int hidden,
                            __half* out) {
     if (batch == 0) return B2LLM_OK;
-    gather_rows_kernel<<<(unsigned)batch, 128, 0, s>>>(x, seq_starts, hidden, out);
+    launch_kernel(gather_rows_kernel, dim3((unsigned)batch), dim3(128), 0, s, x, seq_starts, hidden, out);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -403,8 +415,8 @@ int32_t launch_interleave_blocks(cudaStream_t s, const float* src, int parts, in
     const int64_t n = (int64_t)parts * rows * (cols / 4);
     if (n == 0) return B2LLM_OK;
     const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    interleave_blocks_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src), parts, rows, cols / 4,
-                                                    reinterpret_cast<float4*>(dst));
+    launch_kernel(interleave_blocks_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const float4*>(src), parts, rows, cols / 4,
+                  reinterpret_cast<float4*>(dst));
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

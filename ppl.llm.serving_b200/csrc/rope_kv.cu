@@ -39,6 +39,8 @@ template <int D, bool KV16>
 __global__ void __launch_bounds__(256) rope_kv_append_kernel(RopeKvParams p) {
     constexpr int HALF = D / 2;
     constexpr int CHUNKS = HALF / 8;  // 16-byte chunks per half: 8 (D = 128) or 4 (D = 64)
+    pdl_trigger();
+    pdl_wait();
     const int sub = threadIdx.x & 7;
     const int heads = p.nq + 2 * p.nkv;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // (token, head) index
@@ -169,11 +171,11 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
     const int64_t threads = step->num_tokens * (num_heads + 2 * geom.num_kv_heads) * 8;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
     if (geom.head_dim == 128) {
-        if (kv16) rope_kv_append_kernel<128, true><<<blocks, 256, 0, s>>>(p);
-        else rope_kv_append_kernel<128, false><<<blocks, 256, 0, s>>>(p);
+        if (kv16) launch_kernel(rope_kv_append_kernel<128, true>, dim3(blocks), dim3(256), 0, s, p);
+        else launch_kernel(rope_kv_append_kernel<128, false>, dim3(blocks), dim3(256), 0, s, p);
     } else {
-        if (kv16) rope_kv_append_kernel<64, true><<<blocks, 256, 0, s>>>(p);
-        else rope_kv_append_kernel<64, false><<<blocks, 256, 0, s>>>(p);
+        if (kv16) launch_kernel(rope_kv_append_kernel<64, true>, dim3(blocks), dim3(256), 0, s, p);
+        else launch_kernel(rope_kv_append_kernel<64, false>, dim3(blocks), dim3(256), 0, s, p);
     }
     B2_LAUNCH_CHECK();
     return B2LLM_OK;

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
     extern __shared__ float srow[];
     __shared__ Best sbest[32];
     __shared__ float sred[64];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const float* row = logits + (int64_t)b * stride;
     float T = temps ? temps[b] : 1.0f;
@@ -167,6 +169,8 @@ __global__ void __launch_bounds__(256) penalty_kernel(const float* __restrict__ 
                                                      const int64_t* __restrict__ start_pos, int vocab,
                                                      uint16_t* __restrict__ count_map, int64_t* __restrict__ next_pos,
                                                      float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const int64_t slot = slots[b];
     uint16_t* cnt = count_map + slot * (int64_t)vocab;
@@ -245,9 +249,8 @@ extern "C" int32_t b2llm_sample_topk_topp(void* stream, const float* logits, con
         in_smem = 1;
         B2_ENSURE_DYN_SMEM(sample_kernel, 200 * 1024);  // a per-device attribute (single-process TP: one thread per GPU)
     }
-    sample_kernel<<<batch, kThreads, smem, s>>>(logits, temperatures_optional, top_p_optional, rand_device, vocab_size,
-                                                batch_stride, top_k, default_top_p, default_rand, (float*)workspace,
-                                                output, logprobs, in_smem);
+    launch_kernel(sample_kernel, dim3(batch), dim3(kThreads), smem, s, logits, temperatures_optional, top_p_optional, rand_device,
+                  vocab_size, batch_stride, top_k, default_top_p, default_rand, (float*)workspace, output, logprobs, in_smem);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -280,10 +283,9 @@ extern "C" int32_t b2llm_apply_penalty(void* stream, const float* logits_in, con
             next_pos = it->second;
         }
     }
-    penalty_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(logits_in, temperatures, repetition_penalties,
-                                                           presence_penalties_optional, frequency_penalties_optional,
-                                                           batch_slots, token_inputs, seqstarts, start_pos, vocab_size,
-                                                           penalty_count_map, next_pos, logits_out);
+    launch_kernel(penalty_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, logits_in, temperatures, repetition_penalties,
+                  presence_penalties_optional, frequency_penalties_optional, batch_slots, token_inputs, seqstarts, start_pos,
+                  vocab_size, penalty_count_map, next_pos, logits_out);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

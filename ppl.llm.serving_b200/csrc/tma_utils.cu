@@ -1,5 +1,7 @@
 #include "tma_utils.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace b2llm {
@@ -30,6 +32,14 @@ void init_once() {
     });
 }
 }  // namespace
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("B2LLM_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 bool tma_available() {
     init_once();

@@ -94,10 +94,17 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
     __shared__ float scratch[32];
     __shared__ double dscratch[32];
     __shared__ int s_last;
+    pdl_trigger();
+    pdl_wait();
     uint8_t* mine = c.base[c.rank];
     uint32_t* my_flags = reinterpret_cast<uint32_t*>(mine + L.flags);  // [0, 8): partials ready; [32, 40): rows delivered
     unsigned* counter = reinterpret_cast<unsigned*>(mine + L.flags) + 64;
     unsigned* fault = counter + 1;
+    // phase clocks (ns, %globaltimer) summed over the calls: [0] calls, [1] waiting for the peers' partials, [2] the rows
+    // (loads, norm, stores), [3] waiting for the peers' rows to land here; [4] scratch: when barrier 1 opened
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(mine + L.flags + 512);
+    uint64_t t_start = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) t_start = globaltimer_ns();
 
     // barrier 1: the GEMM before this kernel completed my partials -> tell every rank, wait for every rank
     if (blockIdx.x == 0 && (int)threadIdx.x < c.tp) {
@@ -105,6 +112,12 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + c.rank, epoch);
     }
     wait_flags(my_flags, c.tp, epoch, fault);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint64_t t1 = globaltimer_ns();
+        stats[0] += 1;
+        stats[1] += t1 - t_start;
+        stats[4] = t1;
+    }
 
     const int nvec = hidden >> 3;
     const __half* x_mine = reinterpret_cast<const __half*>(mine + L.x);
@@ -200,12 +213,20 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
     if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
+    uint64_t t_done = 0;
+    if (threadIdx.x == 0) t_done = globaltimer_ns();
     if ((int)threadIdx.x < c.tp) {
         __threadfence_system();
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + 32 + c.rank, epoch);
     }
     wait_flags(my_flags + 32, c.tp, epoch, fault);
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        const uint64_t t_end = globaltimer_ns();
+        const uint64_t t1 = *reinterpret_cast<volatile unsigned long long*>(stats + 4);
+        stats[2] += t_done > t1 ? t_done - t1 : 0;
+        stats[3] += t_end - t_done;
+    }
 }
 
 }  // namespace
@@ -232,11 +253,11 @@ int32_t launch_tp_join(cudaStream_t s, const TpPeers& peers, const TpLayout& L, 
     // every rank launches, also one that owns no row of a small step: the flag barriers are collective
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned, 148 * 4));
     if (mode == 0)
-        tp_join_kernel<0><<<grid, kThreads, 0, s>>>(peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
+        launch_kernel(tp_join_kernel<0>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
     else if (mode == 1)
-        tp_join_kernel<1><<<grid, kThreads, 0, s>>>(peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
+        launch_kernel(tp_join_kernel<1>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
     else
-        tp_join_kernel<2><<<grid, kThreads, 0, s>>>(peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
+        launch_kernel(tp_join_kernel<2>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
