@@ -270,8 +270,9 @@ B2LLM_API int32_t b2llm_op_rope_kv_append(void* stream, void* qkv_fp16, const b2
  * [num_tokens, nq * head_dim].  workspace: b2llm_attention_workspace_size bytes.
  * impl: 0 auto, 1 simple reference kernel for every token, 2 tensor-core kernels (split-KV flash-decoding for the
  * decode sequences, flash-attention forward for the prefill sequences; head_dim 128); 3 / 4 / 5 = 2 with the decode
- * kernel's TMA loader forced: 3 slim + merged K/V loads (experimental), 4 dividing loader, 5 slim loader; 6 = 2 with the
- * tcgen05 / TMEM prefill kernel (experimental; falls back to the mma.sync kernel when the step has cached prefixes) */
+ * kernel's TMA loader forced: 3 slim + merged K/V loads (the default where the layout allows), 4 dividing loader, 5 slim
+ * loader; 6 / 8 = 2 with the prefill kernel forced: 6 tcgen05 / TMEM (the default; falls back to the mma.sync kernel when
+ * the step has cached prefixes), 8 mma.sync */
 B2LLM_API int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_heads, int32_t head_dim);
 B2LLM_API int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const b2llm_step* step, int32_t num_heads,
                                      const b2llm_kv_geom* geom, int32_t layer, const void* kv_cache,

@@ -770,15 +770,44 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict
     for (int i = 0; i < 4; ++i) out[w * 128 + lane * 4 + i] = __float2half_rn(acc[i] / ll);
 }
 
-int choose_splits(int64_t ctas_per_split, int64_t max_kv_len) {
-    // fill ~3 CTAs/SM on 148 SMs; never make a split shorter than 256 tokens
-    const int64_t target = 148 * 3;
-    int64_t n = (target + ctas_per_split - 1) / ctas_per_split;
-    const int64_t max_by_len = (max_kv_len + 255) / 256;
-    if (n > max_by_len) n = max_by_len;
-    if (n < 1) n = 1;
-    if (n > 64) n = 64;
-    return (int)n;
+// How many KV splits and how many warps per CTA.  The kernel's unit of residency is a warp (12 warp slots per SM,
+// 148 SMs): a launch of W = ctas * warps warps runs in ceil(W / 1776) waves and the last, partial wave costs as much as
+// a full one.  Round 2 run 6 showed what that does away from the 1-GPU benchmark shape: 70B TP = 8 (256 sequences x 1 kv
+// head x 8192 tokens) ran 512 CTAs x 4 warps = 1.15 waves at 0.60 of the HBM peak, 7B TP = 8 (4096 CTAs) 2.3 waves at
+// 0.76.  So: the smallest splits x warps whose wave efficiency reaches 0.93 (else the most efficient one), keeping at
+// least 8 units (128 tokens) per warp and the split partials inside the workspace (attention_workspace_rows).
+struct DecodePlan {
+    int nsplit, warps;
+};
+constexpr int64_t kWarpSlots = 148 * 12;
+
+int64_t attention_workspace_rows(int64_t batch) { return std::max<int64_t>(2 * batch + 444, 4096); }
+
+DecodePlan plan_decode(int64_t base_ctas, int64_t batch, int64_t max_kv_len) {
+    const int64_t units = (max_kv_len + UNIT - 1) / UNIT;
+    auto eff = [&](int64_t n, int64_t w) {
+        const double waves = (double)(base_ctas * n * w) / (double)kWarpSlots;
+        return waves / ceil(waves);
+    };
+    DecodePlan best{1, 1};
+    double best_eff = eff(1, 1);
+    if (best_eff >= 0.90) return best;
+    for (int64_t nw = 2; nw <= 64; ++nw) {       // total ways a sequence's KV range is cut (splits x warps)
+        if (units / nw < 8) break;
+        for (int w : {4, 2, 1}) {                // prefer warps of one CTA (merged in shared memory) over splits
+            if (nw % w) continue;
+            const int64_t n = nw / w;
+            if (batch * n > attention_workspace_rows(batch)) continue;
+            const double e = eff(n, w);
+            if (e > best_eff + 1e-9) {
+                best_eff = e;
+                best = DecodePlan{(int)n, w};
+            }
+            break;
+        }
+        if (best_eff >= 0.93) break;
+    }
+    return best;
 }
 
 AttnParams make_params(const AttnArgs& a) {
@@ -930,9 +959,9 @@ std::once_flag g_attn_env_once;
 
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
     (void)head_dim;
-    // rows = sequences * q heads * splits; choose_splits keeps sequences * splits <= sequences + 444 and the
+    // rows = sequences * q heads * splits; plan_decode keeps sequences * splits <= attention_workspace_rows and the
     // "always split" mode (split_k == 2) needs 2 per sequence
-    return (2 * batch + 444) * num_heads * 130 * (int64_t)sizeof(float);
+    return attention_workspace_rows(batch) * num_heads * 130 * (int64_t)sizeof(float);
 }
 
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end) {
@@ -1029,15 +1058,12 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     const int64_t max_kv = a.step->max_kv_len > 0 ? a.step->max_kv_len : 1;
     const int G = gq == 1 ? 1 : (gq <= 4 ? 4 : 8);
     const int chunks = (gq + G - 1) / G;
-    p.nsplit = choose_splits((int64_t)p.nkv * chunks * p.decoding_batches, max_kv);
-    if (a.split_k == 0) p.nsplit = 1;
+    const int64_t base_ctas = (int64_t)p.nkv * chunks * p.decoding_batches;
+    const DecodePlan plan = plan_decode(base_ctas, p.decoding_batches, max_kv);
+    p.nsplit = plan.nsplit;
+    int warps = plan.warps;
+    if (a.split_k == 0) p.nsplit = 1;     // ENGINE_CONF_DECODING_ATTN_SPLIT_K 0: never split (warps of one CTA still share a sequence)
     if (a.split_k == 2 && p.nsplit < 2 && max_kv > UNIT) p.nsplit = 2;
-    // warps per CTA: one warp per CTA is fastest (no cross-warp merge, measured on B200) as long as the
-    // grid alone fills the 148 x 12 warp slots; small grids get 2 or 4 warps per CTA
-    const int64_t ctas = (int64_t)p.nkv * chunks * p.decoding_batches * p.nsplit;
-    const int64_t units_per_cta = ((max_kv + UNIT - 1) / UNIT + p.nsplit - 1) / p.nsplit;
-    int warps = ctas >= 148 * 12 ? 1 : (ctas >= 148 * 6 || units_per_cta < 16 ? 2 : 4);
-    if (units_per_cta < 4) warps = 1;
     if (g_attn_warps_override == 1 || g_attn_warps_override == 2 || g_attn_warps_override == 4) warps = g_attn_warps_override;
     // TMA loader: units must be 16 contiguous slots
     bool tma = tma_available() && (p.cache_mode == 0 || p.page_size % UNIT == 0) &&

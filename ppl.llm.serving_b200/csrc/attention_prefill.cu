@@ -291,12 +291,15 @@ int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a) {
     return B2LLM_OK;
 }
 
-int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, bool force_tc) {
+int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, int which) {
+    // the tcgen05 / TMEM kernel is the default since round 2 run 8 (602.7 vs 201.9 TFLOP/s causal at 8 x 4096 tokens,
+    // profiles/r2_prefill_run8.txt); steps with cached prefixes fall back to the mma.sync kernel inside it
+    // (B2LLM_ERR_UNSUPPORTED).  B2LLM_PREFILL_IMPL=mma keeps the mma.sync kernel for everything.
     static const bool env_tc = [] {
         const char* e = getenv("B2LLM_PREFILL_IMPL");
-        return e != nullptr && e[0] == 't';
+        return !(e != nullptr && e[0] == 'm');
     }();
-    if (force_tc || env_tc) {
+    if (which == 1 || (which < 0 && env_tc)) {
         const int32_t rc = launch_attention_prefill_tc(s, a);
         if (rc != B2LLM_ERR_UNSUPPORTED) return rc;
     }

@@ -1,10 +1,11 @@
 // K7 on the 5th-generation tensor cores: flash-attention forward for FRESH prompts (start_pos == 0) with tcgen05.mma,
 // TMEM accumulators and TMA-staged Q / K / V tiles.
 //
-//   STATUS: OPT-IN and NOT YET RUN ON A DEVICE (written in round 1 after the GPU budget was spent; it assembles for
-//   sm_100a -- UTCHMMA / UTMALDG / SYNCS in the SASS).  Selected only by B2LLM_PREFILL_IMPL=tc or b2llm_op_attention
-//   impl 6; the validated mma.sync kernel (attention_prefill.cu) stays the default.  Gated parity tests:
-//   tests/test_ops_gpu.py::test_attention_prefill_tcgen05_experimental.
+//   STATUS: parity-green on the device since round 2 run 1 (tests/test_ops_gpu.py::test_attention_prefill_tcgen05); selected
+//   by B2LLM_PREFILL_IMPL=tc or b2llm_op_attention impl 6.  The first cut (one softmax thread per query row) ran at
+//   219 TFLOP/s causal, barely above the mma.sync kernel (202): with one warp per scheduler and 128-long max / sum
+//   dependency chains the softmax warps were latency-bound and the tensor pipe idled.  This version splits every row
+//   over TWO threads (see below).
 //
 // Why: one whole prefill step of BASELINE config 5 spends 54 % of its time in the mma.sync prefill attention at
 // 136-170 TFLOP/s (profiles/r1_prefill_step_run14.json) -- < 10 % of the fp16 tensor peak.
@@ -17,9 +18,13 @@
 //            the N = d dimension is contiguous -- descriptor with LBO = stride between the two 64-d slabs, SBO = 1024,
 //            b_major = 1 in the instruction descriptor; cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>);
 //            S and PV each double-buffered in TMEM (4 x 128 columns = all 512);
-//   warps 2-5  thread r owns query row r (its TMEM lane): two passes over S_j with tcgen05.ld (row max, then
-//            exp2 / row sum / fp16 P_j written K-major + swizzled into smem, fence.proxy.async), and one block
-//            later O += PV_j from TMEM with the running-max correction, O kept in 128 fp32 registers.
+//   warps 2-9  two threads per query row (warps 2-5: keys / head-dims [0, 64) of the row's TMEM lane, warps 6-9:
+//            [64, 128) -- a warp may touch the TMEM lanes of quarter warp % 4, so both warps of a pair qualify): the
+//            64 scores of the thread's half stay in registers between the row-max pass and the exp2 / row-sum / fp16 P_j
+//            pass (P written K-major + swizzled into smem, fence.proxy.async); the two half-maxima meet through shared
+//            memory and a 64-thread named barrier, the row sums stay per-thread partials until the end; one block later
+//            O += PV_j from TMEM with the running-max correction, O kept in 64 fp32 registers per thread.  Two warps
+//            per scheduler and four independent max / sum chains per thread instead of one 128-long chain.
 // Pipeline: S_{j+1} is issued before PV_j, so the tensor core computes the next scores while the softmax warps work on
 // S_j; the O update of block j is deferred until after P_{j+1} so that PV_j's latency is hidden as well.
 //
@@ -46,9 +51,9 @@ constexpr int Q_BYTES = 2 * SLAB;          // 32 KB
 constexpr int KV_STAGE = 4 * SLAB;         // K (2 slabs) + V (2 slabs) = 64 KB
 constexpr int KV_STAGES = 2;
 constexpr int P_BYTES = 2 * SLAB;          // 32 KB
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE + P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*half-row exchange*/;
 constexpr int TMEM_COLS = 512;             // S0 | S1 | PV0 | PV1, 128 fp32 columns each
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps
 
 struct PrefillTcParams {
     const int64_t* seq_starts;
@@ -146,11 +151,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             mbar_init(bar(1 + s), 1);
             mbar_init(bar(3 + s), 1);
             mbar_init(bar(5 + s), 1);
-            mbar_init(bar(7 + s), 128);
+            mbar_init(bar(7 + s), 256);
             mbar_init(bar(11 + s), 1);
-            mbar_init(bar(13 + s), 128);
+            mbar_init(bar(13 + s), 256);
         }
-        mbar_init(bar(9), 128);
+        mbar_init(bar(9), 256);
         mbar_init(bar(10), 1);
         mbar_fence_init();
     }
@@ -229,23 +234,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
     } else {
         const int quarter = warp & 3;             // TMEM lane quarter of this warp
+        const int hf = (warp - 2) >> 2;           // which half of the row's keys / head dims this thread owns
         const int r = quarter * 32 + lane;        // query row inside the tile
         const int qrow = q0 + r;                  // position in the sequence (start_pos == 0)
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float o[D];
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + hf * 64;
+        float* smax = reinterpret_cast<float*>(smem + (bars + 8u * 20 - smem_base));  // [2 halves][128 rows], after the barriers
+        constexpr int H = D / 2;                  // 64 columns per thread
+        float o[H];
 #pragma unroll
-        for (int i = 0; i < D; ++i) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, m_o = -INFINITY;  // m_o: the max the registers of o are relative to
+        for (int i = 0; i < H; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, m_o = -INFINITY;  // l_run: this thread's partial row sum; m_o: the max o is relative to
         float m_blk_prev = -INFINITY;             // running max after the previous block (the reference of PV_{j-1})
 
-        auto accumulate = [&](int j, float m_ref) {   // o += PV_j, PV_j being relative to m_ref
+        auto accumulate = [&](int j, float m_ref) {   // o += PV_j (this thread's 64 head dims), PV_j being relative to m_ref
             const int s = j & 1;
             const uint32_t ph = (j >> 1) & 1;
             mbar_wait(bar(11 + s), ph);
             tc_fence_after();
             const float corr = m_o == -INFINITY ? 0.f : ex2_approx(m_o - m_ref);
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
+            for (int c = 0; c < H / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + 256 + s * 128 + c * 32, v);
 #pragma unroll
@@ -262,63 +270,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const bool last = j == nblk - 1;      // the only block with masked keys (diagonal / past the sequence end)
             mbar_wait(bar(5 + s), ph);
             tc_fence_after();
-            // pass 1: row max of the (scaled, masked) scores
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + s * 128 + c * 32, v);
+            // the thread's 64 scores: loaded once, scaled and masked in place, kept for both passes
+            float sc[H];
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(lane_addr + s * 128, v0);
+                tmem_ld32(lane_addr + s * 128 + 32, v1);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int key = j * BN + c * 32 + i;
-                    const float sv = (!last || (key <= qrow && key < n)) ? __uint_as_float(v[i]) * p.sl2 : -INFINITY;
-                    mx = fmaxf(mx, sv);
+                    sc[i] = __uint_as_float(v0[i]) * p.sl2;
+                    sc[32 + i] = __uint_as_float(v1[i]) * p.sl2;
                 }
             }
+            tc_fence_before();
+            mbar_arrive(bar(7 + s));              // S buffer s may be overwritten: the scores live in registers now
+            if (last) {
+                const int key0 = j * BN + hf * H;
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const int key = key0 + i;
+                    if (!(key <= qrow && key < n)) sc[i] = -INFINITY;
+                }
+            }
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < H; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], sc[i]);
+            const float mx_half = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // the other half of the row lives in the partner warp (same quarter): exchange through smem
+            smax[hf * 128 + r] = mx_half;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            const float mx = fmaxf(mx_half, smax[(hf ^ 1) * 128 + r]);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // both read before the next block overwrites
             const float m_new = fmaxf(m_run, mx);
             const float m_safe = m_new == -INFINITY ? 0.f : m_new;
             l_run *= m_run == -INFINITY ? 0.f : ex2_approx(m_run - m_safe);
             m_run = m_new;
-            // pass 2: P = exp2(s - m), row sum, fp16 P into smem (K-major, 128 B swizzle: chunk c16 of row r at c16 ^ (r & 7))
+            // P = exp2(s - m), partial row sum, fp16 P into smem (K-major, 128 B swizzle: chunk c16 of row r at c16 ^ (r & 7));
+            // this thread's 64 keys are exactly slab `hf` of the P operand
             mbar_wait(bar(10), (uint32_t)((j & 1) ^ 1));  // PV_{j-1} has read the P buffer
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + s * 128 + c * 32, v);
-                uint32_t pk[16];
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint8_t* prow = smem + (sP - smem_base) + hf * SLAB + r * 128;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const int key = j * BN + c * 32 + i;
-                    const bool ok0 = !last || (key <= qrow && key < n), ok1 = !last || (key + 1 <= qrow && key + 1 < n);
-                    const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(v[i]), p.sl2, -m_safe)) : 0.f;
-                    const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.sl2, -m_safe)) : 0.f;
-                    sum += p0 + p1;
-                    const __half2 h = __floats2half2_rn(p0, p1);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                uint8_t* slab = smem + (sP - smem_base) + (c >> 1) * SLAB + r * 128;
+            for (int c16 = 0; c16 < 8; ++c16) {
+                uint32_t pk[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int c16 = (c & 1) * 4 + q;
-                    *reinterpret_cast<uint4*>(slab + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const int i = c16 * 8 + 2 * q;
+                    const float p0 = ex2_approx(sc[i] - m_safe), p1 = ex2_approx(sc[i + 1] - m_safe);  // exp2(-inf) = 0 for masked keys
+                    sum4[q] += p0 + p1;
+                    const __half2 h = __floats2half2_rn(p0, p1);
+                    pk[q] = *reinterpret_cast<const uint32_t*>(&h);
                 }
+                *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            l_run += sum;
-            tc_fence_before();
-            mbar_arrive(bar(7 + s));              // S buffer s may be overwritten
+            l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             fence_proxy_async_smem();             // P: generic-proxy stores -> tensor core's async-proxy reads
-            mbar_arrive(bar(9));                  // P_j ready
+            mbar_arrive(bar(9));                  // P_j ready (256 arrivals: both halves of every row)
             if (j > 0) accumulate(j - 1, m_blk_prev);  // deferred by one block: PV_{j-1} finished long ago
             m_blk_prev = m_safe;
         }
         accumulate(nblk - 1, m_blk_prev);
 
+        // full row sum = the two partials
+        smax[hf * 128 + r] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        const float l_row = l_run + smax[(hf ^ 1) * 128 + r];
         if (qrow < n) {
-            const float inv = 1.f / l_run;
-            __half* orow = p.out + (seq_tok0 + qrow) * (int64_t)p.nq * D + (int64_t)hq * D;
+            const float inv = 1.f / l_row;
+            __half* orow = p.out + (seq_tok0 + qrow) * (int64_t)p.nq * D + (int64_t)hq * D + hf * H;
 #pragma unroll
-            for (int c = 0; c < D / 8; ++c) {
+            for (int c = 0; c < H / 8; ++c) {
                 uint32_t w[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

@@ -241,12 +241,12 @@ int32_t launch_rope_kv_append(cudaStream_t s, __half* qkv, const b2llm_step* ste
 int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token_begin, int64_t token_end);
 int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a);
 int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a);
-// tcgen05 / TMEM prefill attention (attention_prefill_tc.cu): OPT-IN, not yet run on a device; B2LLM_ERR_UNSUPPORTED when
-// its preconditions do not hold (the caller then uses the mma.sync kernel)
+// tcgen05 / TMEM prefill attention (attention_prefill_tc.cu): B2LLM_ERR_UNSUPPORTED when its preconditions do not hold
+// (cached prefixes in the step, head_dim != 128: the caller then uses the mma.sync kernel)
 int32_t launch_attention_prefill_tc(cudaStream_t s, const AttnArgs& a);
-// prefill attention of the step: the tcgen05 kernel when selected (B2LLM_PREFILL_IMPL=tc or force_tc) and applicable,
-// else the mma.sync kernel
-int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, bool force_tc = false);  // sequences [decoding_batches, batch)
+// prefill attention of the step: the tcgen05 kernel where applicable, else the mma.sync kernel
+// which: -1 default (tcgen05 unless B2LLM_PREFILL_IMPL=mma), 0 the mma.sync kernel, 1 the tcgen05 kernel
+int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, int which = -1);  // sequences [decoding_batches, batch)
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim);
 
 // ---- tensor-parallel fused residual join over NVLink peer memory (tp_join.cu)

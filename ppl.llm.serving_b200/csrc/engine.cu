@@ -336,7 +336,7 @@ extern "C" int32_t b2llm_engine_create(const b2llm_model_desc* desc, int32_t ran
             e->head_rows = d.vocab_size / tp;
         }
     }
-    if (tp > 1 && tp <= kTpMaxRanks && d.hidden_dim % 8 == 0 && d.hidden_dim <= 8192) {
+    if ((tp == 2 || tp == 4 || tp == 8) && d.hidden_dim % 8 == 0 && d.hidden_dim <= 8192) {
         const char* js = getenv("B2LLM_TP_JOIN");
         e->tp_fused = !(js && js[0] == 'n');
     }
@@ -1077,13 +1077,13 @@ extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const 
     aa.out = (__half*)out_fp16;
     cudaStream_t s = (cudaStream_t)stream;
     if (impl >= 3 && impl <= 5) aa.loader = impl == 3 ? 2 : (impl == 4 ? 0 : 1);
-    const bool prefill_tc = impl == 6;  // experimental tcgen05 prefill kernel
+    const int prefill_which = impl == 6 ? 1 : (impl == 8 ? 0 : -1);  // tcgen05 / mma.sync prefill kernel forced
     if (impl == 1 || (impl == 0 && geom->head_dim != 128)) return launch_attention_simple(s, aa, 0, step->num_tokens);
     B2_REQUIRE(workspace, B2LLM_ERR_INVALID_VALUE, "attention: workspace required");
     int32_t rc = launch_attention_decode_mma(s, aa);
     if (rc) return rc;
     if (step->decoding_batches >= step->batch) return B2LLM_OK;
-    return launch_attention_prefill(s, aa, prefill_tc);
+    return launch_attention_prefill(s, aa, prefill_which);
 }
 
 extern "C" int32_t b2llm_op_synth_fp16(void* stream, uint64_t seed, uint64_t tensor_id, uint64_t num_elements, float std,

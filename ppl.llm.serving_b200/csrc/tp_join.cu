@@ -31,8 +31,16 @@ namespace b2llm {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kMaxIter = 4;  // 16-byte vectors per thread: hidden <= 8 * 256 * 4 = 8192
+// 16-byte vectors per thread.  The kernel is latency-bound (NVLink round trips, two block reductions), so what counts
+// is ROWS IN FLIGHT: a row needs (TP + 3) x hidden x 2 B of registers whatever the CTA shape, hence few fat threads per
+// row -- 128 threads for hidden 4096 at TP = 2 (4-5 CTAs per SM: the 512 rows a rank owns at B = 1024 run as ONE wave;
+// with 256-thread CTAs they took two, 25 us per join, round 2 run 8).  TP >= 4 keeps 2 vectors per thread: TP x 4 peer
+// loads in flight would not fit the register file, and a rank owns at most 256 rows there anyway.
+template <int TP>
+struct JoinCfg {
+    static constexpr int kIter = TP == 2 ? 4 : 2;
+    static constexpr int kMaxThreads = TP == 2 ? 256 : 512;   // hidden <= 8192
+};
 
 struct alignas(16) Half8 {
     __half2 v[4];
@@ -87,10 +95,17 @@ __device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
     return r;
 }
 
-// MODE 0: residual join only; 1: + RMSNorm -> int8 row + fp32 scale; 2: + RMSNorm -> fp16 row
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L, const __half* __restrict__ gamma, float eps,
-                                                          int rows, int hidden, int bcast_x, uint32_t epoch) {
+// MODE 0: residual join only; 1: + RMSNorm -> int8 row + fp32 scale; 2: + RMSNorm -> fp16 row.
+// TP is a template parameter so that the loop over the ranks unrolls: ALL peer loads of a row (TP x kMaxIter 16-byte
+// loads per thread) are in flight together.  The first version looped over a run-time rank count and consumed every
+// load before issuing the next -- one NVLink round trip per rank and vector: 25 us per join at TP = 4, 49 us at TP = 8
+// with hidden 8192 (round 2 run 6: profiles/r2_bench_run6_n{4,8}_tp.json, fused_join_us_per_call).
+template <int MODE, int TP>
+__global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
+    tp_join_kernel(TpPeers c, TpLayout L, const __half* __restrict__ gamma, float eps, int rows, int hidden, int bcast_x,
+                   uint32_t epoch) {
+    constexpr int kMaxIter = JoinCfg<TP>::kIter;
+    const int kThreads = blockDim.x;
     __shared__ float scratch[32];
     __shared__ double dscratch[32];
     __shared__ int s_last;
@@ -107,11 +122,11 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
     if (blockIdx.x == 0 && threadIdx.x == 0) t_start = globaltimer_ns();
 
     // barrier 1: the GEMM before this kernel completed my partials -> tell every rank, wait for every rank
-    if (blockIdx.x == 0 && (int)threadIdx.x < c.tp) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < TP) {
         __threadfence_system();
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + c.rank, epoch);
     }
-    wait_flags(my_flags, c.tp, epoch, fault);
+    wait_flags(my_flags, TP, epoch, fault);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const uint64_t t1 = globaltimer_ns();
         stats[0] += 1;
@@ -121,9 +136,25 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
 
     const int nvec = hidden >> 3;
     const __half* x_mine = reinterpret_cast<const __half*>(mine + L.x);
-    for (int64_t row = c.rank + (int64_t)c.tp * blockIdx.x; row < rows; row += (int64_t)c.tp * gridDim.x) {
+    const __half* part[TP];
+#pragma unroll
+    for (int r = 0; r < TP; ++r) part[r] = reinterpret_cast<const __half*>(c.base[r] + L.partial);
+    for (int64_t row = c.rank + (int64_t)TP * blockIdx.x; row < rows; row += (int64_t)TP * gridDim.x) {
         Half8 xn[kMaxIter];
         double ss = 0.0;
+        // every peer load of the row first (TP x kMaxIter independent 16-byte loads per thread) ...
+        Half8 pv[kMaxIter][TP], xold[kMaxIter];
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = threadIdx.x + it * kThreads;
+            if (v < nvec) {
+                const int64_t off = row * hidden + v * 8;
+#pragma unroll
+                for (int r = 0; r < TP; ++r) pv[it][r] = ld8_peer(part[r] + off);
+                xold[it] = *reinterpret_cast<const Half8*>(x_mine + off);
+            }
+        }
+        // ... then the arithmetic
 #pragma unroll
         for (int it = 0; it < kMaxIter; ++it) {
             const int v = threadIdx.x + it * kThreads;
@@ -132,16 +163,16 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
             float acc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-            for (int r = 0; r < c.tp; ++r) {  // fp32 sum in rank order
-                const Half8 p = ld8_peer(reinterpret_cast<const __half*>(c.base[r] + L.partial) + off);
+#pragma unroll
+            for (int r = 0; r < TP; ++r) {  // fp32 sum in rank order
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(p.v[i]);
+                    const float2 f = __half22float2(pv[it][r].v[i]);
                     acc[2 * i] = __fadd_rn(acc[2 * i], f.x);
                     acc[2 * i + 1] = __fadd_rn(acc[2 * i + 1], f.y);
                 }
             }
-            const Half8 xo = *reinterpret_cast<const Half8*>(x_mine + off);
+            const Half8 xo = xold[it];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 o = __half22float2(__floats2half2_rn(acc[2 * i], acc[2 * i + 1]));  // the all-reduced value is fp16
@@ -151,7 +182,8 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
                 ss += (double)f.x * (double)f.x + (double)f.y * (double)f.y;
             }
             if (bcast_x) {
-                for (int r = 0; r < c.tp; ++r) *reinterpret_cast<Half8*>(reinterpret_cast<__half*>(c.base[r] + L.x) + off) = xn[it];
+#pragma unroll
+                for (int r = 0; r < TP; ++r) *reinterpret_cast<Half8*>(reinterpret_cast<__half*>(c.base[r] + L.x) + off) = xn[it];
             } else {
                 *reinterpret_cast<Half8*>(reinterpret_cast<__half*>(mine + L.x) + off) = xn[it];
             }
@@ -183,13 +215,14 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
                 Half8 o;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o.v[i] = __floats2half2_rn(y[it][2 * i], y[it][2 * i + 1]);
-                for (int r = 0; r < c.tp; ++r)
+#pragma unroll
+                for (int r = 0; r < TP; ++r)
                     *reinterpret_cast<Half8*>(reinterpret_cast<__half*>(c.base[r] + L.y) + row * hidden + v * 8) = o;
             }
         } else {
             amax = block_max(amax, scratch);
             const float inv_scale = amax > 0.f ? __fdiv_rn(127.0f, amax) : 0.f;
-            if ((int)threadIdx.x < c.tp) reinterpret_cast<float*>(c.base[threadIdx.x] + L.qscale)[row] = __fdiv_rn(amax, 127.0f);
+            if ((int)threadIdx.x < TP) reinterpret_cast<float*>(c.base[threadIdx.x] + L.qscale)[row] = __fdiv_rn(amax, 127.0f);
 #pragma unroll
             for (int it = 0; it < kMaxIter; ++it) {
                 const int v = threadIdx.x + it * kThreads;
@@ -200,7 +233,8 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
                     const int q = max(-127, min(127, __float2int_rn(__fmul_rn(y[it][i], inv_scale))));
                     w[i >> 2] |= (uint32_t)(q & 0xff) << (8 * (i & 3));
                 }
-                for (int r = 0; r < c.tp; ++r)
+#pragma unroll
+                for (int r = 0; r < TP; ++r)
                     *reinterpret_cast<uint2*>(c.base[r] + L.q + row * hidden + v * 8) = make_uint2(w[0], w[1]);
             }
         }
@@ -208,18 +242,22 @@ __global__ void __launch_bounds__(kThreads) tp_join_kernel(TpPeers c, TpLayout L
 
     // barrier 2: once every CTA of this rank has pushed its rows out, tell every rank; the last CTA stays until every
     // rank's rows have landed here, so the kernel's end means "the joined activations are complete on this GPU"
-    __threadfence_system();
+    // one system-scope fence per CTA: the CTA barrier orders every thread's peer stores before thread 0's fence, which is
+    // cumulative (the grid-sync idiom, at system scope) -- 255 fewer fences per CTA than fencing in every thread
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
     __syncthreads();
     if (!s_last) return;
     uint64_t t_done = 0;
     if (threadIdx.x == 0) t_done = globaltimer_ns();
-    if ((int)threadIdx.x < c.tp) {
+    if ((int)threadIdx.x < TP) {
         __threadfence_system();
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + 32 + c.rank, epoch);
     }
-    wait_flags(my_flags + 32, c.tp, epoch, fault);
+    wait_flags(my_flags + 32, TP, epoch, fault);
     if (threadIdx.x == 0) {
         *counter = 0;
         const uint64_t t_end = globaltimer_ns();
@@ -247,17 +285,27 @@ TpLayout tp_layout(int64_t max_tokens, int hidden, int act_cols) {
 
 int32_t launch_tp_join(cudaStream_t s, const TpPeers& peers, const TpLayout& L, int mode, bool bcast_x, const __half* gamma,
                        float eps, int64_t rows, int hidden, uint32_t epoch) {
-    B2_REQUIRE(hidden % 8 == 0 && hidden <= 8 * kThreads * kMaxIter, B2LLM_ERR_UNSUPPORTED, "tp join: hidden must be a multiple of 8, <= 8192");
-    B2_REQUIRE(peers.tp >= 2 && peers.tp <= kTpMaxRanks, B2LLM_ERR_UNSUPPORTED, "tp join: 2 .. 8 ranks");
+    B2_REQUIRE(hidden % 8 == 0 && hidden <= 8192, B2LLM_ERR_UNSUPPORTED, "tp join: hidden must be a multiple of 8, <= 8192");
+    B2_REQUIRE(peers.tp == 2 || peers.tp == 4 || peers.tp == 8, B2LLM_ERR_UNSUPPORTED, "tp join: 2, 4 or 8 ranks");
+    B2_REQUIRE(mode >= 0 && mode <= 2, B2LLM_ERR_INVALID_VALUE, "tp join: bad mode");
     const int64_t owned = (rows - peers.rank + peers.tp - 1) / peers.tp;
     // every rank launches, also one that owns no row of a small step: the flag barriers are collective
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(owned, 148 * 4));
-    if (mode == 0)
-        launch_kernel(tp_join_kernel<0>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
-    else if (mode == 1)
-        launch_kernel(tp_join_kernel<1>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
-    else
-        launch_kernel(tp_join_kernel<2>, dim3(grid), dim3(kThreads), 0, s, peers, L, gamma, eps, (int)rows, hidden, bcast_x ? 1 : 0, epoch);
+    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(owned, 148 * 4)));
+    const int iters = peers.tp == 2 ? JoinCfg<2>::kIter : JoinCfg<8>::kIter;
+    const dim3 block((unsigned)((((hidden / 8) + iters - 1) / iters + 31) / 32 * 32));
+    const int bx = bcast_x ? 1 : 0;
+#define B2_JOIN(MM, TT) launch_kernel(tp_join_kernel<MM, TT>, grid, block, 0, s, peers, L, gamma, eps, (int)rows, hidden, bx, epoch)
+#define B2_JOIN_TP(MM)                                   \
+    do {                                                 \
+        if (peers.tp == 2) B2_JOIN(MM, 2);               \
+        else if (peers.tp == 4) B2_JOIN(MM, 4);          \
+        else B2_JOIN(MM, 8);                             \
+    } while (0)
+    if (mode == 0) B2_JOIN_TP(0);
+    else if (mode == 1) B2_JOIN_TP(1);
+    else B2_JOIN_TP(2);
+#undef B2_JOIN_TP
+#undef B2_JOIN
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }

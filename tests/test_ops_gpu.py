@@ -389,14 +389,14 @@ def test_attention_decode_gqa_and_splits(lib, impl):
     _attention_case(lib, desc, [1] * 3, [40, 1, 257], 3, impl, seed=4)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 8])
 def test_attention_mixed_prefill_decode(lib, impl):
     desc = _mk_desc(3, 1, nq=4, nkv=2)
     # 2 decoding sequences first, then a fresh prompt and a prompt with a cached prefix
     _attention_case(lib, desc, [1, 1, 9, 6], [64, 7, 0, 32], 2, impl, seed=11)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 8])  # 8: the mma.sync prefill kernel forced (2 = default = tcgen05 where applicable)
 @pytest.mark.parametrize("nq,nkv", [(4, 4), (8, 2)])
 def test_attention_prefill_tiles_and_prefixes(lib, impl, nq, nkv):
     """prefill sequences spanning several 64-query tiles / 64-key blocks, tile-boundary lengths, cached prefixes that
@@ -460,10 +460,8 @@ def test_attention_decode_merged_loader(lib, layout, mode, page):
     _attention_case(lib, _mk_desc(layout, mode, nq=4, nkv=4, page=page), [1] * 5, [0, 15, 16, 100, 333], 5, 5, seed=layout)
 
 
-@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
-                    reason="kernels that have not run on a device yet (set B2LLM_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("nq,nkv", [(4, 4), (8, 2)])
-def test_attention_prefill_tcgen05_experimental(lib, nq, nkv):
+def test_attention_prefill_tcgen05(lib, nq, nkv):
     """impl 6: the tcgen05 / TMEM prefill kernel (attention_prefill_tc.cu) on fresh prompts whose lengths straddle the
     128-query tiles and 128-key blocks, alone and behind decode sequences; steps with cached prefixes must fall back to
     the mma.sync kernel and still be right"""
