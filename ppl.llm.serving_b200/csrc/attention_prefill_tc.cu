@@ -28,11 +28,8 @@
 // Pipeline: S_{j+1} is issued before PV_j, so the tensor core computes the next scores while the softmax warps work on
 // S_j; the O update of block j is deferred until after P_{j+1} so that PV_j's latency is hidden as well.
 //
-// Numeric contract: oracle/llama_ref.py _attend (fp16 Q/K/V, fp32 scores and sums, P rounded to fp16 for the PV
-// product -- the mma.sync kernel carries P as hi + lo halves).  A numpy emulation of exactly this block schedule on
-// N(0,1) inputs puts the maximum error at 2.1e-4 .. 3.5e-4 of the output scale for prompt lengths 300 .. 4096 with
-// fp16 P and at 2.0e-4 .. 2.8e-4 with hi + lo: the final fp16 rounding of O dominates, so one PV product suffices for
-// the 2e-3 op tolerance (tests/test_ops_gpu.py) -- to be confirmed against the e2e logits tolerance on the device.
+// Numeric contract: oracle/llama_ref.py _attend (fp16 Q/K/V, fp32 scores and sums, P carried as hi + lo fp16 halves
+// for the PV product like the mma.sync kernel: the tensor core sees ~22 bits of P).
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -50,8 +47,9 @@ constexpr int SLAB = BQ * 128;             // 16 KB: 128 rows x 64 fp16 (one 128
 constexpr int Q_BYTES = 2 * SLAB;          // 32 KB
 constexpr int KV_STAGE = 4 * SLAB;         // K (2 slabs) + V (2 slabs) = 64 KB
 constexpr int KV_STAGES = 2;
-constexpr int P_BYTES = 2 * SLAB;          // 32 KB
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE + P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*half-row exchange*/;
+constexpr int P_BYTES = 2 * SLAB;          // 32 KB per P buffer; two of them: P as hi + lo fp16 halves (see below)
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*half-row exchange*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "attn_prefill_tc_kernel: shared memory budget");
 constexpr int TMEM_COLS = 512;             // S0 | S1 | PV0 | PV1, 128 fp32 columns each
 constexpr int NUM_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps
 
@@ -128,7 +126,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t sQ = smem_base, sKV = sQ + Q_BYTES, sP = sKV + KV_STAGES * KV_STAGE;
-    const uint32_t bars = sP + P_BYTES;
+    const uint32_t bars = sP + 2 * P_BYTES;
     // barriers: 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5,6 s_full | 7,8 s_empty | 9 p_full | 10 p_empty | 11,12 o_full | 13,14 o_empty
     auto bar = [&](int i) { return bars + 8u * i; };
     const uint32_t tmem_slot = bars + 8u * 16;
@@ -215,11 +213,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 mbar_wait(bar(13 + s), ph ^ 1);        // PV buffer s consumed
                 tc_fence_after();
                 const uint32_t sV = sKV + s * KV_STAGE + 2 * SLAB;
+                // P = hi + lo (two fp16 halves, ~22 bits): PV_j = P_hi V_j + P_lo V_j into the same accumulator.  With a
+                // single fp16 P the op-level tolerance holds, but end to end the 2^-11 error of P moves the prefill rows by
+                // ~1e-3 and W8A8 re-quantisation carries that into every later step (round 2 run 9: median logits error
+                // 1.7e-3 instead of 1e-6) -- the mma.sync kernel splits P for the same reason.
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k) {
-                    const uint64_t da = desc_kmajor(sP + (k >> 2) * SLAB) + 2 * (k & 3);
-                    const uint64_t db = desc_mnmajor(sV + k * 16 * 128, SLAB);  // 16 keys = 16 rows of 128 B further
-                    tc_mma_f16(tmem_base + 256 + s * 128, da, db, idesc_pv, k != 0 ? 1u : 0u);
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < BN / 16; ++k) {
+                        const uint64_t da = desc_kmajor(sP + half * P_BYTES + (k >> 2) * SLAB) + 2 * (k & 3);
+                        const uint64_t db = desc_mnmajor(sV + k * 16 * 128, SLAB);  // 16 keys = 16 rows of 128 B further
+                        tc_mma_f16(tmem_base + 256 + s * 128, da, db, idesc_pv, (half | k) != 0 ? 1u : 0u);
+                    }
                 }
                 tc_commit(bar(11 + s));           // PV_j complete
                 tc_commit(bar(10));               // P buffer free
@@ -312,16 +317,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             uint8_t* prow = smem + (sP - smem_base) + hf * SLAB + r * 128;
 #pragma unroll
             for (int c16 = 0; c16 < 8; ++c16) {
-                uint32_t pk[4];
+                uint32_t pk[4], pl[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = c16 * 8 + 2 * q;
                     const float p0 = ex2_approx(sc[i] - m_safe), p1 = ex2_approx(sc[i + 1] - m_safe);  // exp2(-inf) = 0 for masked keys
                     sum4[q] += p0 + p1;
                     const __half2 h = __floats2half2_rn(p0, p1);
+                    const float2 hf2 = __half22float2(h);
+                    const __half2 lo = __floats2half2_rn(p0 - hf2.x, p1 - hf2.y);
                     pk[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    pl[q] = *reinterpret_cast<const uint32_t*>(&lo);
                 }
                 *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(prow + P_BYTES + ((c16 ^ (r & 7)) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
             l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             fence_proxy_async_smem();             // P: generic-proxy stores -> tensor core's async-proxy reads

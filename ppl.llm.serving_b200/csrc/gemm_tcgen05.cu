@@ -511,10 +511,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 // straight into the 128-byte-swizzled K-major tile the UMMA descriptor expects, make the writes visible to the async
 // proxy and arrive on the stage's b_full barrier.  One weight tile feeds up to two 128-row A tiles (M <= 256 per
 // CTA, the decode batch of BASELINE config 4 per rank), so the conversion cost is paid once per 256 rows.
-//   warp 0     TMA producer (A tiles + packed W)          warps 2-5   converters (thread = one output channel)
-//   warp 1     TMEM alloc + MMA issuer                    warps 6-9   epilogue (TMEM lane quarter = warp % 4)
+//   warp 0     TMA producer (A tiles + packed W)          warps 2-9   converters (two threads per output channel: the
+//   warp 1     TMEM alloc + MMA issuer                                k-block's elements [0, 32) and [32, 64))
+//                                                         warps 10-13 epilogue (TMEM lane quarter = warp % 4)
+// Eight converter warps, not four: with one warp per scheduler the expansion (a dependent lop / sub / mul / st chain per
+// chunk) was latency-bound and the MMAs waited for it -- 365 TFLOP/s at M = 256 (round 1 run 10).
 constexpr int W4_BN = 128;
-constexpr int W4_THREADS = 320;
+constexpr int W4_THREADS = 448;  // TMA warp, MMA warp, 8 converter warps, 4 epilogue warps
 template <int MT>
 struct CfgW4 {
     static constexpr int STAGES = MT == 2 ? 4 : 5;
@@ -546,7 +549,11 @@ __device__ __forceinline__ uint4 w4_expand8(uint32_t w, __half2 sc) {
 template <int EPI, int MT>
 __global__ void __launch_bounds__(W4_THREADS, 1)
     gemm_w4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                   const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc) {
+                   const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc, int splitk,
+                   float* __restrict__ ws, unsigned* __restrict__ counters) {
+    // splitk > 1 (few output tiles, e.g. qkv of 70B at TP = 8: N = 1280 -> 10 tiles on 148 SMs): a work item is
+    // (tile, k-slice); every item stores its fp32 partial tile to ws[slice][M][N], the LAST item of a tile to finish
+    // (atomic counter) sums the slices in slice order -- deterministic -- and runs the epilogue.
     using C = CfgW4<MT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -564,12 +571,14 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
     const int num_tiles = num_m * num_n;
     const int nk = (2 * K) / BKB;   // k-blocks of 64 elements (128 bytes of fp16)
     const int gpr = K / 128;        // scale groups per output channel
+    const int num_items = num_tiles * splitk;
+    auto kb_begin = [&](int ks) { return (int)((int64_t)nk * ks / splitk); };
     pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(afull_bar(s), 1);
-            mbar_init(bfull_bar(s), 128);
+            mbar_init(bfull_bar(s), 256);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -594,9 +603,10 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
             tma_prefetch_desc(&map_w);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int tile = item / splitk, ks = item - tile * splitk;
                 const int m_blk = tile % num_m, n_blk = tile / num_m;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb_begin(ks); kb < kb_begin(ks + 1); ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sraw = sa + C::A_BYTES;
                     mbar_expect_tx(afull_bar(stage), C::A_BYTES + C::RAW_BYTES);
@@ -614,13 +624,15 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int ks = item % splitk;
+                const int kb0 = kb_begin(ks), kb1 = kb_begin(ks + 1);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_c = tmem_base + acc * (MT * W4_BN);
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(afull_bar(stage), phase);
                     mbar_wait(bfull_bar(stage), phase);
                     tc_fence_after();
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
                         const uint64_t da = make_smem_desc(sa + mt * BM * BKB);
 #pragma unroll
                         for (int k = 0; k < BKB / 32; ++k)
-                            tc_mma<false>(tmem_c + mt * W4_BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            tc_mma<false>(tmem_c + mt * W4_BN, da + 2 * k, db + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -639,31 +651,35 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
                 tc_commit(tfull_bar(acc));
             }
         }
-    } else if (warp < 6) {
-        // converters: thread r owns output channel (row) r of the weight tile
-        const int r = threadIdx.x - 64;
+    } else if (warp < 10) {
+        // converters: threads (r, hf) own output channel (row) r of the weight tile, hf = which 32 of the k-block's 64 elements
+        const int r = (threadIdx.x - 64) & 127, hf = (threadIdx.x - 64) >> 7;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int tile = item / splitk, ks = item - tile * splitk;
             const int n_blk = tile / num_m;
+            const int kb0 = kb_begin(ks), kb1 = kb_begin(ks + 1);
             const __half* srow = w_scale + (int64_t)(n_blk * W4_BN + r) * gpr;
-            for (int kb = 0; kb < nk; ++kb) {
+            __half sc_next = srow[kb0 >> 1];
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const __half sc1 = sc_next;          // 64-element k-blocks, 128-element groups; next group's scale is
+                if (kb + 1 < kb1) sc_next = srow[(kb + 1) >> 1];  // requested before this block's data arrives
                 mbar_wait(afull_bar(stage), phase);
                 const uint32_t sraw = smem_base + stage * C::STAGE_BYTES + C::A_BYTES, sb = sraw + C::RAW_BYTES;
-                const __half sc1 = srow[kb >> 1];  // 64-element k-blocks, 128-element groups
                 const __half2 sc = __halves2half2(sc1, sc1);
-                uint4 raw[2];
+                uint4 raw;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                             : "r"(sraw + r * 32 + hf * 16));
+                const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint4 v[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(raw[j].x), "=r"(raw[j].y), "=r"(raw[j].z), "=r"(raw[j].w)
-                                 : "r"(sraw + r * 32 + j * 16));
-                const uint32_t wds[8] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w, raw[1].x, raw[1].y, raw[1].z, raw[1].w};
+                for (int c = 0; c < 4; ++c) v[c] = w4_expand8(wds[c], sc);  // 16-byte chunk 4 hf + c = elements [8 (4 hf + c), + 8)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {  // 16-byte chunk c = elements [8c, 8c + 8) of the k-block
-                    const uint4 v = w4_expand8(wds[c], sc);
-                    const uint32_t dst = sb + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t dst = sb + (uint32_t)(r * 128 + (((4 * hf + c) ^ (r & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w) : "memory");
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(bfull_bar(stage));
@@ -672,8 +688,10 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
         }
     } else {
         const int quarter = warp & 3;
+        __shared__ int s_last_item;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            const int tile = item / splitk, ks = item - tile * splitk;
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -688,11 +706,54 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
                     const int n0 = n_blk * W4_BN + c * 32;
                     uint32_t rr[32];
                     tmem_ld32(taddr + c * 32, rr);
-                    if (m < M) epilogue_store32<false, EPI>(rr, m, n0, 1.f, nullptr, out, ldc);
+                    if (splitk == 1) {
+                        if (m < M) epilogue_store32<false, EPI>(rr, m, n0, 1.f, nullptr, out, ldc);
+                    } else if (m < M) {  // this slice's partial sums
+                        float4* dst = reinterpret_cast<float4*>(ws + ((int64_t)ks * M + m) * N + n0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            dst[q] = make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]), __uint_as_float(rr[4 * q + 2]),
+                                                 __uint_as_float(rr[4 * q + 3]));
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
+            if (splitk > 1) {
+                // the tile's last slice to arrive sums all slices (in slice order) and runs the epilogue
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+                if (threadIdx.x == W4_THREADS - 128) s_last_item = atomicAdd(counters + tile, 1u) == (unsigned)(splitk - 1) ? 1 : 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_last_item) {
+                    __threadfence();
+#pragma unroll 1
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int m = (m_blk * MT + mt) * BM + quarter * 32 + lane;
+                        if (m >= M) continue;
+#pragma unroll 1
+                        for (int c = 0; c < W4_BN / 32; ++c) {
+                            const int n0 = n_blk * W4_BN + c * 32;
+                            float sum[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+                            for (int k2 = 0; k2 < splitk; ++k2) {
+                                const float4* src = reinterpret_cast<const float4*>(ws + ((int64_t)k2 * M + m) * N + n0);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 v = __ldcg(src + q);
+                                    sum[4 * q] += v.x; sum[4 * q + 1] += v.y; sum[4 * q + 2] += v.z; sum[4 * q + 3] += v.w;
+                                }
+                            }
+                            uint32_t rr[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(sum[i]);
+                            epilogue_store32<false, EPI>(rr, m, n0, 1.f, nullptr, out, ldc);
+                        }
+                    }
+                    if (threadIdx.x == W4_THREADS - 128) counters[tile] = 0;  // ready for the next launch
+                }
+            }
         }
     }
 
@@ -804,6 +865,38 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
     return launch<I8, EPI, 128>(s, a, a_scale, w, w_scale, M, N, Kb, out, ldc);
 }
 
+// split-K scratch of the W4A16 kernel, one per (device, stream): fp32 partial tiles + one counter per output tile
+struct W4Scratch {
+    float* ws = nullptr;
+    unsigned* counters = nullptr;
+    size_t ws_floats = 0;
+};
+constexpr int kW4MaxTiles = 4096;
+std::map<std::pair<int, cudaStream_t>, W4Scratch> g_w4_scratch;
+
+int32_t w4_scratch(cudaStream_t s, size_t floats, W4Scratch* out) {
+    int dev = 0;
+    B2_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    W4Scratch& sc = g_w4_scratch[{dev, s}];
+    if (!sc.counters) {
+        B2_CHECK_CUDA(cudaMalloc(&sc.counters, kW4MaxTiles * sizeof(unsigned)));
+        B2_CHECK_CUDA(cudaMemset(sc.counters, 0, kW4MaxTiles * sizeof(unsigned)));
+    }
+    if (floats > sc.ws_floats) {
+        if (sc.ws) {
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
+            cudaFree(sc.ws);
+        }
+        sc.ws = nullptr;
+        sc.ws_floats = 0;
+        B2_CHECK_CUDA(cudaMalloc(&sc.ws, floats * sizeof(float)));
+        sc.ws_floats = floats;
+    }
+    *out = sc;
+    return B2LLM_OK;
+}
+
 template <int EPI, int MT>
 int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __half* scale, int64_t M, int N, int K, void* out,
                   int64_t ldc) {
@@ -829,8 +922,18 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     }
     const int tiles = (int)((M + MT * BM - 1) / (MT * BM)) * (N / W4_BN);
     const int sms = gemm_sm_budget();
-    const int grid = tiles < sms ? tiles : sms;
-    launch_kernel(kern, dim3(grid), dim3(W4_THREADS), C::SMEM_BYTES, s, ma, mw, scale, (int)M, N, K, out, ldc);
+    // split-K when the tiles alone leave most of the machine idle: slices of >= 8 k-blocks, about one work item per SM
+    const int nk = (2 * K) / BKB;
+    int splitk = 1;
+    if (tiles * 2 <= sms && tiles <= kW4MaxTiles) splitk = std::max(1, std::min(sms / tiles, nk / 8));
+    W4Scratch sc{};
+    if (splitk > 1) {
+        const int32_t rc = w4_scratch(s, (size_t)splitk * (size_t)M * (size_t)N, &sc);
+        if (rc) return rc;
+    }
+    const int items = tiles * splitk;
+    const int grid = items < sms ? items : sms;
+    launch_kernel(kern, dim3(grid), dim3(W4_THREADS), C::SMEM_BYTES, s, ma, mw, scale, (int)M, N, K, out, ldc, splitk, sc.ws, sc.counters);
     B2_LAUNCH_CHECK();
     return B2LLM_OK;
 }
@@ -850,7 +953,10 @@ int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* pac
     if (M == 0) return B2LLM_OK;
     const __half* sc = (const __half*)scale_fp16;
     // two A tiles per weight tile halve the conversion work, but only pay once the grid still fills half the machine
-    const bool two = M > BM && ((M + 2 * BM - 1) / (2 * BM)) * (N / W4_BN) >= gemm_sm_budget() / 2;
+    // two A tiles per weight tile halve the conversion work: worth it when the grid still fills half the machine, or
+    // when the tiles are so few that split-K fills it anyway
+    const int tiles2 = (int)((M + 2 * BM - 1) / (2 * BM)) * (N / W4_BN);
+    const bool two = M > BM && (tiles2 >= gemm_sm_budget() / 2 || tiles2 * 4 <= gemm_sm_budget());
     switch (epilogue) {
         case EPI_F16: return two ? launch_w4<EPI_F16, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_F16, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
         case EPI_RESIDUAL: return two ? launch_w4<EPI_RESIDUAL, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_RESIDUAL, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
