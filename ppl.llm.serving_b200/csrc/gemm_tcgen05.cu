@@ -335,6 +335,10 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): warms the weight tiles a ring fill ahead
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // same barrier offset in both CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -421,6 +425,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 tma_load_2d_pair(smem_base + kb * C::STAGE_BYTES + C::A_BYTES, &map_w, mapa_u32(full_bar(kb), 0), kb * BKB,
                                  (pair / num_m) * BN2 + (int)rank * (BN2 / 2));
             }
+            // L2 prefetch distance.  At M = 1024 only four CTA pairs share a weight tile and they run in lock step, so every
+            // weight load is an HBM miss; six 32 KB stages buy ~1.8 us of look-ahead, less than the loaded HBM latency, and the
+            // tensor pipe sat at 50-53 % (profiles/r2_ncu_step_run9.txt; 87 % at M = 8192 where the tiles come from L2).  The
+            // producer therefore asks L2 for the weight tile kPF k-blocks ahead of the one it stages.
+            constexpr int kPF = 16;
+            auto prefetch_w = [&](int g) {   // g-th k-block of this pair's sequence of tiles
+                const int it2 = g / nk, kb2 = g - it2 * nk;
+                const int tile2 = pair + it2 * num_pairs;
+                if (tile2 < num_tiles) tma_prefetch_l2_2d(&map_w, kb2 * BKB, (tile2 / num_m) * BN2 + (int)rank * (BN2 / 2));
+            };
+            for (int g = pre; g < kPF; ++g) prefetch_w(g);
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
@@ -430,6 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
                 const int row_a = m_blk * 2 * BM + (int)rank * BM;
                 const int row_w = n_blk * BN2 + (int)rank * (BN2 / 2);
                 for (int kb = 0; kb < nk; ++kb, ++done) {
+                    prefetch_w(done + kPF);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint32_t fb = mapa_u32(full_bar(stage), 0);
                     if (done >= pre) {
@@ -550,10 +566,11 @@ template <int EPI, int MT>
 __global__ void __launch_bounds__(W4_THREADS, 1)
     gemm_w4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                    const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc, int splitk,
-                   float* __restrict__ ws, unsigned* __restrict__ counters) {
+                   float* __restrict__ ws) {
     // splitk > 1 (few output tiles, e.g. qkv of 70B at TP = 8: N = 1280 -> 10 tiles on 148 SMs): a work item is
-    // (tile, k-slice); every item stores its fp32 partial tile to ws[slice][M][N], the LAST item of a tile to finish
-    // (atomic counter) sums the slices in slice order -- deterministic -- and runs the epilogue.
+    // (tile, k-slice); every item stores its fp32 partial tile to ws[slice][M][N] and w4_splitk_reduce_kernel sums the
+    // slices in slice order -- deterministic -- and applies the epilogue.  (A first version let the last item of a tile
+    // do that inside this kernel: 10 CTAs reducing 18 MB with row-strided loads took 209 us, round 2 run 10.)
     using C = CfgW4<MT>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -688,7 +705,6 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
         }
     } else {
         const int quarter = warp & 3;
-        __shared__ int s_last_item;
         int it = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int tile = item / splitk, ks = item - tile * splitk;
@@ -719,41 +735,6 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
-            if (splitk > 1) {
-                // the tile's last slice to arrive sums all slices (in slice order) and runs the epilogue
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-                if (threadIdx.x == W4_THREADS - 128) s_last_item = atomicAdd(counters + tile, 1u) == (unsigned)(splitk - 1) ? 1 : 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (s_last_item) {
-                    __threadfence();
-#pragma unroll 1
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const int m = (m_blk * MT + mt) * BM + quarter * 32 + lane;
-                        if (m >= M) continue;
-#pragma unroll 1
-                        for (int c = 0; c < W4_BN / 32; ++c) {
-                            const int n0 = n_blk * W4_BN + c * 32;
-                            float sum[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) sum[i] = 0.f;
-                            for (int k2 = 0; k2 < splitk; ++k2) {
-                                const float4* src = reinterpret_cast<const float4*>(ws + ((int64_t)k2 * M + m) * N + n0);
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 v = __ldcg(src + q);
-                                    sum[4 * q] += v.x; sum[4 * q + 1] += v.y; sum[4 * q + 2] += v.z; sum[4 * q + 3] += v.w;
-                                }
-                            }
-                            uint32_t rr[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(sum[i]);
-                            epilogue_store32<false, EPI>(rr, m, n0, 1.f, nullptr, out, ldc);
-                        }
-                    }
-                    if (threadIdx.x == W4_THREADS - 128) counters[tile] = 0;  // ready for the next launch
-                }
-            }
         }
     }
 
@@ -762,6 +743,51 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
+}
+
+// out = epilogue(sum over slices of ws[slice][m][n]), 8 consecutive columns per thread (coalesced float4 loads)
+template <int EPI>
+__global__ void __launch_bounds__(256) w4_splitk_reduce_kernel(const float* __restrict__ ws, int splitk, int M, int N,
+                                                               void* __restrict__ out, int64_t ldc) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n8 = N >> 3;
+    if (idx >= (int64_t)M * n8) return;
+    const int m = (int)(idx / n8), n0 = (int)(idx - (int64_t)m * n8) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    for (int k = 0; k < splitk; ++k) {
+        const float4* src = reinterpret_cast<const float4*>(ws + ((int64_t)k * M + m) * N + n0);
+        const float4 a = __ldcg(src), b = __ldcg(src + 1);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+        v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if constexpr (EPI == EPI_SWIGLU) {
+        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + (n0 >> 1);
+        const __half2 h0 = __floats2half2_rn(silu_mul_f32(v[0], v[1]), silu_mul_f32(v[2], v[3]));
+        const __half2 h1 = __floats2half2_rn(silu_mul_f32(v[4], v[5]), silu_mul_f32(v[6], v[7]));
+        *reinterpret_cast<uint2*>(orow) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    } else {
+        __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + n0;
+        uint32_t w[4];
+        uint4 old = make_uint4(0, 0, 0, 0);
+        if constexpr (EPI == EPI_RESIDUAL) old = *reinterpret_cast<const uint4*>(orow);
+        const uint32_t* ow = reinterpret_cast<const uint32_t*>(&old);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = v[2 * j], b = v[2 * j + 1];
+            if constexpr (EPI == EPI_RESIDUAL) {
+                const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ow[j]));
+                a = __fadd_rn(o2.x, a);
+                b = __fadd_rn(o2.y, b);
+            }
+            const __half2 h = __floats2half2_rn(a, b);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(orow) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -868,10 +894,8 @@ int32_t pick_bn(cudaStream_t s, const void* a, const float* a_scale, const void*
 // split-K scratch of the W4A16 kernel, one per (device, stream): fp32 partial tiles + one counter per output tile
 struct W4Scratch {
     float* ws = nullptr;
-    unsigned* counters = nullptr;
     size_t ws_floats = 0;
 };
-constexpr int kW4MaxTiles = 4096;
 std::map<std::pair<int, cudaStream_t>, W4Scratch> g_w4_scratch;
 
 int32_t w4_scratch(cudaStream_t s, size_t floats, W4Scratch* out) {
@@ -879,10 +903,6 @@ int32_t w4_scratch(cudaStream_t s, size_t floats, W4Scratch* out) {
     B2_CHECK_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_map_mutex);
     W4Scratch& sc = g_w4_scratch[{dev, s}];
-    if (!sc.counters) {
-        B2_CHECK_CUDA(cudaMalloc(&sc.counters, kW4MaxTiles * sizeof(unsigned)));
-        B2_CHECK_CUDA(cudaMemset(sc.counters, 0, kW4MaxTiles * sizeof(unsigned)));
-    }
     if (floats > sc.ws_floats) {
         if (sc.ws) {
             B2_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -925,7 +945,7 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     // split-K when the tiles alone leave most of the machine idle: slices of >= 8 k-blocks, about one work item per SM
     const int nk = (2 * K) / BKB;
     int splitk = 1;
-    if (tiles * 2 <= sms && tiles <= kW4MaxTiles) splitk = std::max(1, std::min(sms / tiles, nk / 8));
+    if (tiles * 2 <= sms) splitk = std::max(1, std::min(sms / tiles, nk / 8));
     W4Scratch sc{};
     if (splitk > 1) {
         const int32_t rc = w4_scratch(s, (size_t)splitk * (size_t)M * (size_t)N, &sc);
@@ -933,8 +953,14 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     }
     const int items = tiles * splitk;
     const int grid = items < sms ? items : sms;
-    launch_kernel(kern, dim3(grid), dim3(W4_THREADS), C::SMEM_BYTES, s, ma, mw, scale, (int)M, N, K, out, ldc, splitk, sc.ws, sc.counters);
+    launch_kernel(kern, dim3(grid), dim3(W4_THREADS), C::SMEM_BYTES, s, ma, mw, scale, (int)M, N, K, out, ldc, splitk, sc.ws);
     B2_LAUNCH_CHECK();
+    if (splitk > 1) {
+        const int64_t threads = M * (N / 8);
+        launch_kernel(w4_splitk_reduce_kernel<EPI>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, s, (const float*)sc.ws, splitk,
+                      (int)M, N, out, ldc);
+        B2_LAUNCH_CHECK();
+    }
     return B2LLM_OK;
 }
 
