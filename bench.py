@@ -455,7 +455,7 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
             else:
                 for _ in range(args.warmup):
                     run.device_step()
-                js = (C.c_double * 4)()
+                js = (C.c_double * 8)()
                 run.lib.b2llm_engine_tp_join_stats(run.res.engine, js)   # reset: count the timed loop only
                 ms = run.time_device(args.steps, barrier)
                 run.lib.b2llm_engine_tp_join_stats(run.res.engine, js)
@@ -484,7 +484,10 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
                     entry["fused_join_us_per_call"] = {"calls_per_step": js[0] / args.steps,
                                                        "waiting_for_peers_partials (rank skew)": js[1] / js[0] * 1e-3,
                                                        "reduce_norm_quant_deliver": js[2] / js[0] * 1e-3,
-                                                       "waiting_for_peers_rows": js[3] / js[0] * 1e-3}
+                                                       "waiting_for_peers_rows": js[3] / js[0] * 1e-3,
+                                                       "first_row_of_cta0": {"peer_loads": js[5] / js[0] * 1e-3,
+                                                                             "reduce_quant_issue_stores": js[6] / js[0] * 1e-3,
+                                                                             "system_fence": js[7] / js[0] * 1e-3}}
                     entry["exchange"] = "fused all-reduce + residual + RMSNorm + quant kernel over NVLink peer memory (csrc/tp_join.cu)"
                 else:
                     entry["exchange"] = "ncclAllReduce + separate residual / RMSNorm / quant kernels (B2LLM_TP_JOIN=nccl)"

@@ -202,10 +202,12 @@ B2LLM_API int32_t b2llm_engine_profile(b2llm_engine* e, int32_t enable);
 B2LLM_API int32_t b2llm_engine_profile_read(b2llm_engine* e, double* ms_by_class, int64_t* count_by_class,
                                             int32_t num_classes);
 /* tensor parallelism: phase clocks of the fused residual-join kernel (csrc/tp_join.cu) accumulated since the last
- * call, read from the device and reset: out4 = { calls, ns waiting for the peers' partial sums (rank skew), ns
- * reducing / normalising / delivering this rank's rows, ns waiting for the peers' rows to land }.  Zeros when the
- * engine is not tensor parallel or uses the ncclAllReduce path (B2LLM_TP_JOIN=nccl). */
-B2LLM_API int32_t b2llm_engine_tp_join_stats(b2llm_engine* e, double* out4);
+ * call, read from the device and reset: out8 = { calls, ns waiting for the peers' partial sums (rank skew), ns
+ * reducing / normalising / delivering this rank's rows, ns waiting for the peers' rows to land, (scratch), and for the
+ * first row of CTA 0: ns until its peer loads arrived, ns of reductions + quantisation + issuing the peer stores, ns in
+ * the system-scope fence }.  Zeros when the engine is not tensor parallel or uses the ncclAllReduce path
+ * (B2LLM_TP_JOIN=nccl). */
+B2LLM_API int32_t b2llm_engine_tp_join_stats(b2llm_engine* e, double* out8);
 /* debugging / parity: copy an intermediate of the last forward to the host.
  * what: 0 residual stream fp16 [num_tokens, hidden] after the last layer; 1 qkv fp16 (last layer, after
  * rope); 2 attention output fp16 (last layer); 3 logits fp32 [batch, vocab] */

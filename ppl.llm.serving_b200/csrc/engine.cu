@@ -976,15 +976,15 @@ extern "C" int32_t b2llm_engine_profile_read(b2llm_engine* e, double* ms_by_clas
 
 extern "C" int64_t b2llm_engine_last_launch_count(const b2llm_engine* e) { return e ? e->last_launches : 0; }
 
-extern "C" int32_t b2llm_engine_tp_join_stats(b2llm_engine* e, double* out4) {
-    B2_REQUIRE(e && out4, B2LLM_ERR_INVALID_VALUE, "tp_join_stats: null argument");
-    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+extern "C" int32_t b2llm_engine_tp_join_stats(b2llm_engine* e, double* out8) {
+    B2_REQUIRE(e && out8, B2LLM_ERR_INVALID_VALUE, "tp_join_stats: null argument");
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
     if (!e->tp_fused || !e->cbuf.p) return B2LLM_OK;
-    unsigned long long h[4];
+    unsigned long long h[8];
     B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
     B2_CHECK_CUDA(cudaMemcpy(h, (uint8_t*)e->cbuf.p + e->comm_layout.flags + 512, sizeof(h), cudaMemcpyDeviceToHost));
     B2_CHECK_CUDA(cudaMemset((uint8_t*)e->cbuf.p + e->comm_layout.flags + 512, 0, sizeof(h)));
-    for (int i = 0; i < 4; ++i) out4[i] = (double)h[i];
+    for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
     return B2LLM_OK;
 }
 

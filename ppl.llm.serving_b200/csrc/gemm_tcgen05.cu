@@ -31,8 +31,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BKB = 128;          // bytes of K per stage = one 128 B swizzle atom = 4 UMMA k-steps
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;      // warps 2..5 are the epilogue
+// warps 2..9 are the epilogue: two warps per TMEM lane quarter (warp % 4), each draining half of the tile's columns.  With
+// four warps -- one per scheduler -- the epilogue was latency-bound (~8 us per 256 x 256 tile, ~14 us with SwiGLU) and at
+// M = 1024, where a CTA pair computes only 1..5 tiles, it was a fixed cost on top of every GEMM: measured times fit
+// "main loop at the M = 8192 rate + 11 us" for qkv / o / down and "5 x epilogue" for gate_up (round 2 run 11).
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARP0 = 2;
+constexpr int EPI_THREADS = 256;
 
 template <int BN>
 struct Cfg {
@@ -104,12 +109,18 @@ template <bool I8, int EPI>
 __device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], int m, int n0, float sa_m,
                                                  const float* __restrict__ w_scale, void* __restrict__ out, int64_t ldc) {
     float v[32];
+    if constexpr (I8) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if constexpr (I8)
-            v[i] = dequant((int)r[i], sa_m, __ldg(w_scale + n0 + i));
-        else
-            v[i] = __uint_as_float(r[i]);
+        for (int q = 0; q < 8; ++q) {  // the 32 channel scales as eight 16-byte broadcast loads
+            const float4 ws4 = __ldg(reinterpret_cast<const float4*>(w_scale + n0) + q);
+            v[4 * q] = dequant((int)r[4 * q], sa_m, ws4.x);
+            v[4 * q + 1] = dequant((int)r[4 * q + 1], sa_m, ws4.y);
+            v[4 * q + 2] = dequant((int)r[4 * q + 2], sa_m, ws4.z);
+            v[4 * q + 3] = dequant((int)r[4 * q + 3], sa_m, ws4.w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     }
     if constexpr (EPI == EPI_F16 || EPI == EPI_RESIDUAL) {
         __half* orow = reinterpret_cast<__half*>(out) + (int64_t)m * ldc + n0;
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), EPI_THREADS);
         }
         mbar_fence_init();
     }
@@ -269,8 +280,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const int m = m_blk * BM + quarter * 32 + lane;
             const float sa_m = (I8 && m < M) ? a_scale[m] : 1.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the tile's 32-column chunks this warp drains
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
                 const int n0 = n_blk * BN + c * 32;
                 if (n0 >= N) break;  // warp-uniform
                 uint32_t r[32];
@@ -400,7 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 256);  // 128 epilogue threads of each CTA
+            mbar_init(tempty_bar(a), 2 * EPI_THREADS);  // the epilogue threads of both CTAs
         }
         mbar_fence_init();
     }
@@ -498,8 +510,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const int m = m_blk * 2 * BM + (int)rank * BM + quarter * 32 + lane;
             const float sa_m = (I8 && m < M) ? a_scale[m] : 1.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
+            const int chalf = (warp - EPI_WARP0) >> 2;
 #pragma unroll 1
-            for (int c = 0; c < BN2 / 32; ++c) {
+            for (int c = chalf * (BN2 / 64); c < (chalf + 1) * (BN2 / 64); ++c) {
                 const int n0 = n_blk * BN2 + c * 32;
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
     unsigned* counter = reinterpret_cast<unsigned*>(mine + L.flags) + 64;
     unsigned* fault = counter + 1;
     // phase clocks (ns, %globaltimer) summed over the calls: [0] calls, [1] waiting for the peers' partials, [2] the rows
-    // (loads, norm, stores), [3] waiting for the peers' rows to land here; [4] scratch: when barrier 1 opened
+    // (loads, norm, stores), [3] waiting for the peers' rows to land here; [4] scratch: when barrier 1 opened; CTA 0's first
+    // row in detail: [5] peer loads, [6] reductions + quantisation + issuing the peer stores, [7] the system-scope fence
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(mine + L.flags + 512);
     uint64_t t_start = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) t_start = globaltimer_ns();
@@ -155,6 +156,9 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
             }
         }
         // ... then the arithmetic
+        const bool clocked = blockIdx.x == 0 && threadIdx.x == 0 && row == c.rank;  // CTA 0's first row carries the fine clocks
+        uint64_t tc0 = 0, tc1 = 0, tc2 = 0;
+        if (clocked) tc0 = globaltimer_ns();
 #pragma unroll
         for (int it = 0; it < kMaxIter; ++it) {
             const int v = threadIdx.x + it * kThreads;
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
             }
         }
         if constexpr (MODE == 0) continue;
+        if (clocked) tc1 = globaltimer_ns();   // the peer loads have arrived (the sums above consumed them)
         ss = block_sum_f64(ss, dscratch);
         const float var = (float)(ss / (double)hidden);
         const float inv = __fdiv_rn(1.0f, sqrtf(__fadd_rn(var, eps)));
@@ -238,6 +243,11 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
                     *reinterpret_cast<uint2*>(c.base[r] + L.q + row * hidden + v * 8) = make_uint2(w[0], w[1]);
             }
         }
+        if (clocked) {
+            tc2 = globaltimer_ns();            // norm, quantisation and the peer stores are issued
+            stats[5] += tc1 - tc0;
+            stats[6] += tc2 - tc1;
+        }
     }
 
     // barrier 2: once every CTA of this rank has pushed its rows out, tell every rank; the last CTA stays until every
@@ -246,7 +256,9 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
     // cumulative (the grid-sync idiom, at system scope) -- 255 fewer fences per CTA than fencing in every thread
     __syncthreads();
     if (threadIdx.x == 0) {
+        const uint64_t tf0 = blockIdx.x == 0 ? globaltimer_ns() : 0;
         __threadfence_system();
+        if (blockIdx.x == 0) stats[7] += globaltimer_ns() - tf0;   // how long the system-scope fence holds CTA 0
         s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
     }
     __syncthreads();

@@ -480,9 +480,11 @@ int32_t PmxLlama::ForEachWeight(const Sink& sink, std::string* err) {
     // every rank -- a row gather reads only the step's tokens, so nothing is gained by splitting it; assembled once, here.
     auto put_assembled = [&](int32_t kind, const Tensor* mine, int split) -> bool {
         if (split == 0 || tp_ == 1) return put(kind, 0, mine);
-        if (kind == B2LLM_W_LM_HEAD && split == 2) {
+        // the engine's own rule for a vocab-parallel head (csrc/engine.cu: vocab / tp a multiple of 32, B2LLM_TP_HEAD != whole)
+        const char* hs = getenv("B2LLM_TP_HEAD");
+        if (kind == B2LLM_W_LM_HEAD && split == 2 && (V / tp_) % 32 == 0 && !(hs && hs[0] == 'w')) {
             if (put(kind, 0, mine)) return true;
-            rc = 0;  // the engine keeps the head whole: assemble it below
+            rc = 0;  // refused after all: assemble it below
             err->clear();
         }
         full.assign(V * h, 0);

@@ -48,7 +48,7 @@ def fnv1a(a: np.ndarray) -> str:
 
 
 def small_desc(**kw):
-    return ModelDesc(64, 96, 2, 4, kw.pop("num_kv_heads", 4), 80, cache_layout=kw.pop("cache_layout", 3),
+    return ModelDesc(64, 96, 2, 4, kw.pop("num_kv_heads", 4), kw.pop("vocab_size", 80), cache_layout=kw.pop("cache_layout", 3),
                      cache_mode=kw.pop("cache_mode", 1), page_size=kw.pop("page_size", 16), max_position=256, **kw)
 
 
@@ -108,6 +108,22 @@ def test_tensor_parallel_slices_gqa(hostlib, tmp_path, emb_split, head_split):
         assert rc == 0, info
         check_desc(info, desc, tp=2, rank=r)
         check_weights(info, expected_weights(desc, w, r, 2))
+
+
+def test_vocab_parallel_lm_head_is_passed_through(hostlib, tmp_path):
+    """vocab 128 at tp = 2: vocab / tp = 64 is a multiple of 32, so the engine's lm head is vocab-parallel and the loader hands
+    every rank ITS [vocab / tp, hidden] slice of output.weight as the export stores it (no re-assembly); the embedding is
+    still assembled whole.  (vocab 80 in the test above: 40 rows per rank -> the head stays whole and is assembled.)"""
+    desc = small_desc(num_kv_heads=2, vocab_size=128)
+    w = SynthWeights(desc, 13)
+    W.write_pmx_export(tmp_path, desc, w, tensor_parallel_size=2, emb_split="hidden", head_split="vocab")
+    for r in range(2):
+        rc, info = inspect(hostlib, tmp_path / f"model_slice_{r}" / "model.onnx")
+        assert rc == 0, info
+        exp = expected_weights(desc, w, r, 2)
+        head = np.asarray(w.lm_head(), np.float16)[r * 64:(r + 1) * 64]
+        exp[2] = (KIND["LM_HEAD"], 0, head)
+        check_weights(info, exp)
 
 
 def test_split_qkv_external_data(hostlib, tmp_path):
