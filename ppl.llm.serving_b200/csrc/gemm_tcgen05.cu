@@ -992,10 +992,15 @@ int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* pac
     if (M == 0) return B2LLM_OK;
     const __half* sc = (const __half*)scale_fp16;
     // two A tiles per weight tile halve the conversion work, but only pay once the grid still fills half the machine
-    // two A tiles per weight tile halve the conversion work: worth it when the grid still fills half the machine, or
-    // when the tiles are so few that split-K fills it anyway
+    // two A tiles per weight tile (MT = 2) halve the conversion work per flop; split-K refills the machine when that leaves
+    // few tiles.  It pays while a work item still runs a long K loop -- measured at M = 256 (round 2 run 17): gate_up
+    // (64 k-blocks per item) 69.4 -> 52.7 us, down (28) 32.8 -> 31.1, but o (8) 14.7 -> 19.6 and qkv (9 vs 18) 20.5 -> 23.1.
+    const int sms_w4 = gemm_sm_budget();
+    const int nk_w4 = (2 * K) / BKB;
     const int tiles2 = (int)((M + 2 * BM - 1) / (2 * BM)) * (N / W4_BN);
-    const bool two = M > BM && (tiles2 >= gemm_sm_budget() / 2 || tiles2 * 4 <= gemm_sm_budget());
+    const int split2 = tiles2 * 2 <= sms_w4 ? std::max(1, std::min(sms_w4 / tiles2, nk_w4 / 8)) : 1;
+    static const int force_mt = [] { const char* e = getenv("B2LLM_W4_MT"); return e ? atoi(e) : 0; }();  // 1 / 2: force (experiments)
+    const bool two = M > BM && (force_mt == 2 || (force_mt != 1 && nk_w4 / split2 >= 24));
     switch (epilogue) {
         case EPI_F16: return two ? launch_w4<EPI_F16, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_F16, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);
         case EPI_RESIDUAL: return two ? launch_w4<EPI_RESIDUAL, 2>(s, a_fp16, packed, sc, M, N, K, out, ldc) : launch_w4<EPI_RESIDUAL, 1>(s, a_fp16, packed, sc, M, N, K, out, ldc);

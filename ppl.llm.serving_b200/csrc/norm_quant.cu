@@ -355,15 +355,17 @@ __global__ void __launch_bounds__(256) interleave_blocks_kernel(const float4* __
     }
 }
 
-// Which row kernel: CTA-per-row wins at decode sizes (rows = running batch ~ 1e3: run 12), the register-resident
-// warp-per-row variants at prefill sizes (65 536 rows: 74 vs 89 ms of norm / quant / rope time per 32-layer step, run 16).
-// Results are bit-identical.  B2LLM_ROW_KERNELS=reg / legacy forces one of them.
+// Which row kernel: the register-resident warp-group-per-row variants from 256 rows up -- at prefill sizes they save
+// 16 % of the norm / quant / rope time (65 536 rows: 74 vs 89 ms per 32-layer step, round 1 run 16), at the decode size
+// (1024 rows) 0.4 % of the step (37.36 vs 37.52 ms, same box back to back, round 2 run 16; round 1 had measured them
+// slower there, before PDL); tiny steps keep the CTA-per-row kernels.  Results are bit-identical (tests cover both at
+// both sizes).  B2LLM_ROW_KERNELS=reg / legacy forces one of them.
 bool use_row_reg(int64_t rows) {
     static const int mode = [] {
         const char* e = getenv("B2LLM_ROW_KERNELS");
         return e == nullptr ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'l' ? 2 : 0));
     }();
-    return mode == 1 || (mode == 0 && rows >= 8192);
+    return mode == 1 || (mode == 0 && rows >= 256);
 }
 
 }  // namespace

@@ -119,7 +119,7 @@ def test_gemm_w4a16_fused(lib, M, N, K):
     np.testing.assert_allclose(out3.cpu().numpy().astype(np.float32), exp3, rtol=3e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("rows,hidden", [(1, 256), (37, 4096), (5, 5120), (3, 11008)])
+@pytest.mark.parametrize("rows,hidden", [(1, 256), (37, 4096), (5, 5120), (3, 11008), (300, 4096), (257, 8192), (1024, 512)])
 def test_rmsnorm_quant(lib, rows, hidden):
     rng = np.random.default_rng(rows * 7 + hidden)
     x = rng.standard_normal((rows, hidden)).astype(np.float16)
@@ -138,9 +138,10 @@ def test_rmsnorm_quant(lib, rows, hidden):
     assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
 
 
-def test_rmsnorm_skip_and_fp16_out(lib):
+@pytest.mark.parametrize("rows", [9, 300])  # CTA-per-row kernels / register-resident kernels
+def test_rmsnorm_skip_and_fp16_out(lib, rows):
     rng = np.random.default_rng(5)
-    rows, hidden = 9, 512
+    hidden = 512
     x = rng.standard_normal((rows, hidden)).astype(np.float16)
     sk = rng.standard_normal((rows, hidden)).astype(np.float16)
     g = (1 + 0.02 * rng.standard_normal(hidden)).astype(np.float16)
@@ -154,7 +155,7 @@ def test_rmsnorm_skip_and_fp16_out(lib):
     np.testing.assert_allclose(y.cpu().numpy().astype(np.float32), ey, rtol=2e-3, atol=1e-3)  # fp16 output rounding
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 128), (33, 4096), (4, 11008)])
+@pytest.mark.parametrize("rows,cols", [(1, 128), (33, 4096), (4, 11008), (300, 11008), (1024, 4096)])  # >= 256 rows: register-resident kernels
 def test_quant_rows_bit_exact(lib, rows, cols):
     rng = np.random.default_rng(cols)
     x = rng.standard_normal((rows, cols)).astype(np.float16)
