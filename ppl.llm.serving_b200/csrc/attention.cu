@@ -957,6 +957,12 @@ std::once_flag g_attn_env_once;
 
 }  // namespace
 
+void attention_decode_plan(int64_t base_ctas, int64_t batch, int64_t max_kv_len, int* nsplit, int* warps) {
+    const DecodePlan p = plan_decode(base_ctas, batch, max_kv_len);
+    *nsplit = p.nsplit;
+    *warps = p.warps;
+}
+
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim) {
     (void)head_dim;
     // rows = sequences * q heads * splits; plan_decode keeps sequences * splits <= attention_workspace_rows and the

@@ -248,6 +248,8 @@ int32_t launch_attention_prefill_tc(cudaStream_t s, const AttnArgs& a);
 // which: -1 default (tcgen05 unless B2LLM_PREFILL_IMPL=mma), 0 the mma.sync kernel, 1 the tcgen05 kernel
 int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, int which = -1);  // sequences [decoding_batches, batch)
 int64_t attention_workspace_bytes(int64_t batch, int num_heads, int head_dim);
+// the decode kernel's launch plan for `base_ctas` = sequences x kv heads x q-head chunks (host logic, no device needed)
+void attention_decode_plan(int64_t base_ctas, int64_t batch, int64_t max_kv_len, int* nsplit, int* warps);
 
 // ---- tensor-parallel fused residual join over NVLink peer memory (tp_join.cu)
 constexpr int kTpMaxRanks = 8;

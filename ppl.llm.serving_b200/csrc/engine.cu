@@ -241,7 +241,27 @@ int32_t map_comm(b2llm_engine* e) {
     e->ipc_opened.clear();
     B2_CHECK_CUDA(cudaMemsetAsync(e->cbuf.p, 0, 1024, e->stream));  // flags, CTA counter, fault word
     const int32_t rc = tp_comm_exchange(e->stream, e->comm, g_nccl_allgather, e->rank, e->tp, e->cbuf.p, &e->peers, &e->ipc_opened);
-    if (rc) return rc;
+    // every rank must take the same path: agree on the outcome (a rank without peer access / IPC would otherwise run
+    // ncclAllReduce against peers spinning in the fused kernel).  MIN over the ranks of "mapping succeeded".
+    int ok = rc == B2LLM_OK ? 1 : 0;
+    if (const char* t = getenv("B2LLM_TP_TEST_FAIL_MAP")) {  // test hook: pretend THIS rank could not map its peers
+        if (atoi(t) == e->rank) ok = 0;
+    }
+    int* flag = reinterpret_cast<int*>((uint8_t*)e->cbuf.p + 768);
+    B2_REQUIRE(g_nccl_allreduce != nullptr, B2LLM_ERR_UNSUPPORTED, "tensor parallel: ncclAllReduce unavailable");
+    B2_CHECK_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    const int nr = g_nccl_allreduce(flag, flag, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, e->comm, e->stream);
+    B2_REQUIRE(nr == 0, B2LLM_ERR_DEVICE, "ncclAllReduce failed with code " + std::to_string(nr));
+    B2_CHECK_CUDA(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    B2_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    if (!ok) {
+        // some rank could not map its peers: the whole group falls back to ncclAllReduce + separate kernels for good
+        // (the activation buffers stay where they are: windows of this rank's own communication buffer)
+        fprintf(stderr, "b2llm: rank %d: peer mapping of the tensor-parallel buffers failed on some rank (%s) -- using ncclAllReduce\n",
+                e->rank, rc ? g_last_error.c_str() : "another rank");
+        e->tp_fused = false;
+        return B2LLM_OK;
+    }
     e->epoch = 0;
     e->comm_mapped = true;
     return B2LLM_OK;
@@ -820,6 +840,7 @@ extern "C" int32_t b2llm_engine_forward(b2llm_engine* e, const b2llm_step* st, f
     bool fused = tp && e->tp_fused;
     if (fused && !e->comm_mapped) {
         if ((rc = map_comm(e))) return rc;
+        fused = e->tp_fused;  // false if the group agreed to fall back to NCCL
     }
     const int join_mode = i8 ? 1 : 2;      // what the fused join leaves for the next block: int8 + scale, or fp16
     bool have_norm = false;                 // the fused join already wrote norm(x) of the upcoming block into a8 / y16
@@ -1058,6 +1079,20 @@ extern "C" int32_t b2llm_op_rope_kv_append(void* stream, void* qkv_fp16, const b
 
 extern "C" int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_heads, int32_t head_dim) {
     return attention_workspace_bytes(batch, num_heads, head_dim);
+}
+
+extern "C" int32_t b2llm_attention_decode_plan(int64_t decoding_batches, int32_t num_heads, int32_t num_kv_heads, int64_t max_kv_len,
+                                               int32_t* nsplit, int32_t* warps) {
+    B2_REQUIRE(nsplit && warps && decoding_batches > 0 && num_kv_heads > 0 && num_heads % num_kv_heads == 0 && max_kv_len > 0,
+               B2LLM_ERR_INVALID_VALUE, "attention_decode_plan: bad arguments");
+    const int gq = num_heads / num_kv_heads;
+    const int G = gq == 1 ? 1 : (gq <= 4 ? 4 : 8);
+    const int chunks = (gq + G - 1) / G;
+    int n = 1, w = 1;
+    attention_decode_plan((int64_t)num_kv_heads * chunks * decoding_batches, decoding_batches, max_kv_len, &n, &w);
+    *nsplit = n;
+    *warps = w;
+    return B2LLM_OK;
 }
 
 extern "C" int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const b2llm_step* step, int32_t num_heads,

@@ -54,6 +54,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// release / acquire fence at system scope (lighter than __threadfence_system(), which is sequentially consistent)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -123,10 +125,9 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
     if (blockIdx.x == 0 && threadIdx.x == 0) t_start = globaltimer_ns();
 
     // barrier 1: the GEMM before this kernel completed my partials -> tell every rank, wait for every rank
-    if (blockIdx.x == 0 && (int)threadIdx.x < TP) {
-        __threadfence_system();
+    // (the partials were written by the kernel before this one: complete and visible; the release store orders them)
+    if (blockIdx.x == 0 && (int)threadIdx.x < TP)
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + c.rank, epoch);
-    }
     wait_flags(my_flags, TP, epoch, fault);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const uint64_t t1 = globaltimer_ns();
@@ -257,18 +258,19 @@ __global__ void __launch_bounds__(JoinCfg<TP>::kMaxThreads, TP == 2 ? 2 : 1)
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint64_t tf0 = blockIdx.x == 0 ? globaltimer_ns() : 0;
-        __threadfence_system();
+        fence_acq_rel_sys();
         if (blockIdx.x == 0) stats[7] += globaltimer_ns() - tf0;   // how long the system-scope fence holds CTA 0
         s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+        if (s_last) fence_acq_rel_sys();  // acquire side of the other CTAs' "fence; atomicAdd"
     }
     __syncthreads();
     if (!s_last) return;
     uint64_t t_done = 0;
     if (threadIdx.x == 0) t_done = globaltimer_ns();
-    if ((int)threadIdx.x < TP) {
-        __threadfence_system();
+    // every CTA fenced its peer stores at system scope before its atomicAdd, and this CTA observed all of them through the
+    // counter: a release store is all the flag needs
+    if ((int)threadIdx.x < TP)
         st_release_sys(reinterpret_cast<uint32_t*>(c.base[threadIdx.x] + L.flags) + 32 + c.rank, epoch);
-    }
     wait_flags(my_flags + 32, TP, epoch, fault);
     if (threadIdx.x == 0) {
         *counter = 0;

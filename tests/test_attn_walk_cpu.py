@@ -72,3 +72,42 @@ def test_incremental_walk_contiguous_index_mode(warps):
             got = issued_slots_walk(0, 16, idx, 2, 0, 0, units_total, warps, warp)
             want = [(u, unit_slot0(0, 16, idx, 2, 0, u)) for u in range(warp, units_total, warps)]
             assert got == want
+
+
+def test_decode_plan_wave_efficiency():
+    """host logic of the decode attention launch (csrc/attention.cu plan_decode), through the C ABI without a device: the
+    kernel's unit of residency is a warp (148 SMs x 12 slots = 1776); a plan is (KV splits, warps per CTA).  Properties:
+    big grids are left alone; shapes that would run in a poorly filled last wave get split until the wave efficiency is
+    >= 0.9 where the sequence length allows; at least 8 units (128 tokens) per warp; partials fit the workspace."""
+    import ctypes as C
+    import b200_import
+    b200_import.load()
+    from ppl_llm_serving_b200 import capi
+    lib = capi.load_library()
+
+    def plan(batch, nq, nkv, kv):
+        n, w = C.c_int32(), C.c_int32()
+        assert lib.b2llm_attention_decode_plan(batch, nq, nkv, kv, C.byref(n), C.byref(w)) == 0
+        return n.value, w.value
+
+    def eff(batch, nq, nkv, kv):
+        n, w = plan(batch, nq, nkv, kv)
+        gq = nq // nkv
+        G = 1 if gq == 1 else (4 if gq <= 4 else 8)
+        warps = nkv * -(-gq // G) * batch * n * w
+        waves = warps / 1776
+        return waves / -(-warps // 1776), n, w
+
+    assert plan(1024, 32, 32, 512) == (1, 1)                      # the 1-GPU benchmark shape: 18.45 waves, untouched
+    assert plan(1024, 16, 16, 512) == (1, 1)                      # TP = 2: 9.2 waves
+    e, n, w = eff(1024, 4, 4, 512)                                # 7B TP = 8: 2.3 waves alone (0.77)
+    assert e >= 0.9 and n * w > 1
+    e, n, w = eff(256, 8, 1, 8192)                                # 70B TP = 8: 256 CTAs
+    assert e >= 0.9 and 8192 // 16 // (n * w) >= 8
+    assert 256 * n <= max(2 * 256 + 444, 4096)                    # split partials fit attention_workspace_rows
+    for batch, nq, nkv, kv in [(1, 32, 32, 17), (3, 8, 2, 300), (48, 4, 4, 400), (7, 64, 8, 4096), (2000, 40, 40, 33)]:
+        n, w = plan(batch, nq, nkv, kv)
+        assert n >= 1 and w in (1, 2, 4)
+        units = -(-kv // 16)
+        assert n * w == 1 or units // (n * w) >= 8
+        assert batch * n <= max(2 * batch + 444, 4096)

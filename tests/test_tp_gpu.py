@@ -26,7 +26,10 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir, quant, join):
     sys.path.insert(0, str(ROOT))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), B2LLM_TP_JOIN=join)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      B2LLM_TP_JOIN="fused" if join == "failmap" else join)
+    if join == "failmap":  # rank 1 "cannot map its peers": the group must agree to fall back to ncclAllReduce
+        os.environ["B2LLM_TP_TEST_FAIL_MAP"] = "1"
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -70,8 +73,7 @@ def _worker(rank, world, port, out_dir, quant, join):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("join", ["fused", "nccl"])
-@pytest.mark.parametrize("quant", [1, 0, 2])
+@pytest.mark.parametrize("quant,join", [(1, "fused"), (1, "nccl"), (0, "fused"), (0, "nccl"), (2, "fused"), (2, "nccl"), (1, "failmap")])
 def test_tensor_parallel_2gpu_matches_tp_oracle(tmp_path, quant, join):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
