@@ -377,7 +377,7 @@ def test_reference_prefix_cache_benchmark_tool_runs(tmp_path):
     (tmp_path / "tokenizer.model").write_text("b2llm-byte-level-tokenizer\n")
     r = _run([tool, "--model-dir", mdir, "--model-param-path", mdir / "params.json", "--tokenizer-path",
               tmp_path / "tokenizer.model", "--quant-method", "online_i8i8", "--max-tokens-scale", "0.01",
-              "--max-running-batch", "16", "--max-tokens-per-step", "4096", "--enable-prefix-cache", "1"], log="INFO")
+              "--max-running-batch", "16", "--max-tokens-per-step", "4096", "--enable-prefix-cache"], log="INFO")  # bool flags take no value
     assert r.returncode == 0, r.stderr[-3000:]
     out = dict(l.split(": ") for l in r.stdout.strip().splitlines() if ": " in l)
     assert "first ttft" in out and "prefix ttft" in out, r.stdout
