@@ -366,8 +366,6 @@ def test_reference_generator_prefix_cache_hit(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
-@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
-                    reason="not yet run on a device (set B2LLM_TEST_EXPERIMENTAL=1); compiled and linked by `make ref`")
 def test_reference_prefix_cache_benchmark_tool_runs(tmp_path):
     """tools/benchmark_prefix_cache_offline.cc, unchanged: 3 warm-ups, one ~1700-character prompt
     generated twice with --enable-prefix-cache; the second pass must hit the cache and report a smaller TTFT"""
@@ -386,8 +384,6 @@ def test_reference_prefix_cache_benchmark_tool_runs(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
-@pytest.mark.skipif(os.environ.get("B2LLM_TEST_EXPERIMENTAL") != "1",
-                    reason="not yet run on a device (set B2LLM_TEST_EXPERIMENTAL=1)")
 def test_reference_offline_inference_with_trained_sentencepiece_model(tmp_path):
     """offline_inference end to end with a REAL sentencepiece model (LLaMA-style BPE with byte fallback, trained here) and a
     model whose vocabulary is the tokenizer's: prompts are tokenised by host/src/sentencepiece.cc, every generated id
