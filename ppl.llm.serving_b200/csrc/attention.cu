@@ -1071,6 +1071,12 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
     if (a.split_k == 0) p.nsplit = 1;     // ENGINE_CONF_DECODING_ATTN_SPLIT_K 0: never split (warps of one CTA still share a sequence)
     if (a.split_k == 2 && p.nsplit < 2 && max_kv > UNIT) p.nsplit = 2;
     if (g_attn_warps_override == 1 || g_attn_warps_override == 2 || g_attn_warps_override == 4) warps = g_attn_warps_override;
+    {   // B2LLM_ATTN_SPLITS: force the number of KV splits (experiments; must fit the workspace)
+        static const int splits_override = [] { const char* e = getenv("B2LLM_ATTN_SPLITS"); return e ? atoi(e) : 0; }();
+        if (splits_override >= 1 && splits_override <= 64 &&
+            (int64_t)p.decoding_batches * splits_override <= attention_workspace_rows(p.decoding_batches))
+            p.nsplit = splits_override;
+    }
     // TMA loader: units must be 16 contiguous slots
     bool tma = tma_available() && (p.cache_mode == 0 || p.page_size % UNIT == 0) &&
                (int64_t)a.geom.max_tokens * a.geom.num_layers * 2 < (1ll << 31);

@@ -19,15 +19,21 @@ from ppl_llm_serving_b200 import capi  # noqa: E402
 from ppl_llm_serving_b200.engine import _ptr  # noqa: E402
 
 lib = capi.load_library()
-B, KV, H, D, L, PAGE = 1024, int(os.environ.get("KV", 512)), 32, 128, 32, 16
+# B, H (q heads), HKV (kv heads), KV: the per-rank shapes of the tensor-parallel configs can be timed on one GPU, e.g.
+#   7B TP 8: H=4 HKV=4;  70B TP 8: B=256 H=8 HKV=1 KV=8192;  13B TP 4: B=512 H=10 HKV=10 KV=2640
+# B2LLM_ATTN_SPLITS / B2LLM_ATTN_WARPS override the kernel's launch plan (plan_decode) for experiments.
+B, KV, D, PAGE = int(os.environ.get("B", 1024)), int(os.environ.get("KV", 512)), 128, 16
+HQ = int(os.environ.get("H", 32))
+H = int(os.environ.get("HKV", HQ))
 T = B * KV
+L = max(1, min(32, int(12e9 // (2 * H * T * D * 1.25))))   # layers of cache to cycle through (<= 12 GB)
 geom = capi.KvGeomC()
 geom.num_layers, geom.num_kv_heads, geom.head_dim, geom.quant_group = L, H, D, 8
 geom.cache_layout, geom.cache_mode, geom.page_size, geom.max_tokens = 3, 1, PAGE, T
 cache = torch.randint(-127, 128, (L * 2 * H * T * D,), dtype=torch.int8, device="cuda")
 scale = torch.full((L * 2 * H * T * D // 8,), 0.01, dtype=torch.float16, device="cuda")
-qkv = torch.randn((B, 3 * H * D), dtype=torch.float16, device="cuda")
-out = torch.empty((B, H * D), dtype=torch.float16, device="cuda")
+qkv = torch.randn((B, (HQ + 2 * H) * D), dtype=torch.float16, device="cuda")
+out = torch.empty((B, HQ * D), dtype=torch.float16, device="cuda")
 rng = np.random.default_rng(0)
 pages_per = KV // PAGE
 perm = rng.permutation(B * pages_per)
@@ -41,12 +47,12 @@ st.token_ids, st.seq_starts, st.kv_starts = tok.data_ptr(), seq_starts.data_ptr(
 st.cache_indices, st.start_pos = page_list.data_ptr(), start_pos.data_ptr()
 st.num_tokens, st.batch, st.decoding_batches = B, B, B
 st.max_seq_len, st.max_kv_len, st.max_pages = 1, KV, pages_per
-ws = torch.empty(lib.b2llm_attention_workspace_size(B, H, D), dtype=torch.uint8, device="cuda")
+ws = torch.empty(lib.b2llm_attention_workspace_size(B, HQ, D), dtype=torch.uint8, device="cuda")
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def run(layer):
-    rc = lib.b2llm_op_attention(sp, _ptr(qkv), C.byref(st), H, C.byref(geom), layer, _ptr(cache), _ptr(scale), _ptr(ws), _ptr(out), 2)
+    rc = lib.b2llm_op_attention(sp, _ptr(qkv), C.byref(st), HQ, C.byref(geom), layer, _ptr(cache), _ptr(scale), _ptr(ws), _ptr(out), 2)
     assert rc == 0, lib.b2llm_last_error()
 
 
@@ -65,6 +71,10 @@ t1.record()
 torch.cuda.synchronize()
 ms = np.array([a.elapsed_time(b) for a, b in evs])
 bytes_per = B * KV * 2 * H * D * 1.25
+ns, nw = C.c_int32(), C.c_int32()
+lib.b2llm_attention_decode_plan(B, HQ, H, KV, C.byref(ns), C.byref(nw))
+print(f"B={B} H={HQ}/{H} KV={KV} plan(default)=({ns.value} splits, {nw.value} warps) "
+      f"override=({os.environ.get('B2LLM_ATTN_SPLITS', '-')}, {os.environ.get('B2LLM_ATTN_WARPS', '-')}) ", end="")
 print(f"attention alone: per-launch median {np.median(ms):.4f} ms min {ms.min():.4f} max {ms.max():.4f}; "
       f"loop avg {t0.elapsed_time(t1) / (reps * L):.4f} ms -> {bytes_per / (t0.elapsed_time(t1) / (reps * L) * 1e-3) / 1e9:.0f} GB/s "
       f"(median {bytes_per / (np.median(ms) * 1e-3) / 1e9:.0f} GB/s)")
