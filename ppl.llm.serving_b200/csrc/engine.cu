@@ -274,7 +274,7 @@ int32_t tp_join(b2llm_engine* e, int mode, bool bcast_x, const __half* gamma, in
 
 }  // namespace
 
-extern "C" const char* b2llm_version(void) { return "b2llm 0.1 (sm_100a)"; }
+extern "C" const char* b2llm_version(void) { return "b2llm 0.2 (sm_100a)"; }
 extern "C" const char* b2llm_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int32_t b2llm_rope_table(int32_t max_position, int32_t head_dim, float theta, float* cos_host,

@@ -76,11 +76,29 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const float* __restric
     // pass 1: arg-max + log-sum-exp of l' = l / T
     Best best{-INFINITY, 0x7fffffff};
     float m = -INFINITY, s = 0.f;
-    for (int i = threadIdx.x; i < vocab; i += kThreads) {
-        const float v = __fdiv_rn(row[i], T);
-        if (row_in_smem) srow[i] = v;
-        if (v > best.v) { best.v = v; best.i = i; }
-        if (v > m) { s = s * __expf(m - v) + 1.f; m = v; } else { s += __expf(v - m); }
+    if ((vocab & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        // 16-byte loads, one running-max update per four logits: the row (128 KB at vocab 32000) is read once and this
+        // kernel is the step's host/device join (round 1: 80 us for 131 MB = 25 % of the HBM peak with scalar loads)
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (int i4 = threadIdx.x; i4 < (vocab >> 2); i4 += kThreads) {
+            const float4 r4 = row4[i4];
+            const float v[4] = {__fdiv_rn(r4.x, T), __fdiv_rn(r4.y, T), __fdiv_rn(r4.z, T), __fdiv_rn(r4.w, T)};
+            const int i = i4 << 2;
+            if (row_in_smem) *reinterpret_cast<float4*>(srow + i) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (v[j] > best.v) { best.v = v[j]; best.i = i + j; }
+            const float vmax = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+            if (vmax > m) { s *= __expf(m - vmax); m = vmax; }
+            s += (__expf(v[0] - m) + __expf(v[1] - m)) + (__expf(v[2] - m) + __expf(v[3] - m));
+        }
+    } else {
+        for (int i = threadIdx.x; i < vocab; i += kThreads) {
+            const float v = __fdiv_rn(row[i], T);
+            if (row_in_smem) srow[i] = v;
+            if (v > best.v) { best.v = v; best.i = i; }
+            if (v > m) { s = s * __expf(m - v) + 1.f; m = v; } else { s += __expf(v - m); }
+        }
     }
     Best top = block_best(best, sbest);
     {   // block log-sum-exp
