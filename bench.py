@@ -623,8 +623,8 @@ def main():
             "roofline": {"kernel": "attn_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None,  # not measured in this run; see traffic_reference_capture
-                         "traffic_reference_capture": "profiles/r2_ncu_step_run9.txt: 5390160000 B dram read+write per launch at this shape "
-                                                      "(ncu --set full, LOADER 3, round 2 run 9) vs 5368709120 algorithmic = 1.004x",
+                         "traffic_reference_capture": "profiles/r2_ncu_step_run25.txt: 5389960000 B dram read+write per launch at this shape "
+                                                      "(ncu --set full, LOADER 3, round 2 run 25) vs 5368709120 algorithmic = 1.004x",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": attn_bytes, "avg_launch_ms": attn_ms,
                          "launches_timed": int(cls_n[0] * min(args.steps, 5))},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
