@@ -30,9 +30,9 @@ from oracle.weights import ModelDesc, SynthWeights, synth_tensor  # noqa: E402
 OUT = ROOT / "tests" / "golden"
 
 
-def small_desc(quant_method=1, layout=3, mode=1, kvh=4):
+def small_desc(quant_method=1, layout=3, mode=1, kvh=4, kvbit=8):
     return ModelDesc(256, 512, 2, 4, kvh, 512, cache_layout=layout, cache_mode=mode, page_size=16,
-                     quant_method=quant_method, max_position=128)
+                     quant_method=quant_method, max_position=128, cache_quant_bit=kvbit, cache_quant_group=8 if kvbit else 1)
 
 
 def gen_step_fixture(name, desc):
@@ -69,7 +69,7 @@ def gen_step_fixture(name, desc):
     rec["kv_cache_final"], rec["kv_scale_final"] = c, s
     rec["desc"] = np.asarray([desc.hidden_dim, desc.intermediate_dim, desc.num_layers, desc.num_heads, desc.num_kv_heads,
                               desc.vocab_size, desc.cache_layout, desc.cache_mode, desc.page_size, desc.quant_method,
-                              desc.max_position], np.int64)
+                              desc.max_position, desc.cache_quant_bit, desc.cache_quant_group], np.int64)
     np.savez_compressed(OUT / f"{name}.npz", **rec)
 
 
@@ -135,6 +135,7 @@ def main():
     gen_ops_fixture()
     gen_step_fixture("step_w8a8_paged_l3", small_desc(1, 3, 1))
     gen_step_fixture("step_fp16_contig_l1_gqa", small_desc(0, 1, 0, kvh=2))
+    gen_step_fixture("step_w8a8_fp16kv_paged_l2_gqa", small_desc(1, 2, 1, kvh=2, kvbit=0))   # cache_quant_bit 0: fp16 cache
     gen_host_kat()
     for f in sorted(OUT.iterdir()):
         print(f.name, f.stat().st_size)

@@ -18,12 +18,12 @@ GOLD = Path(__file__).resolve().parent / "golden"
 
 
 def _desc_from(arr):
-    h, inter, L, nh, nkv, V, layout, mode, ps, qm, mp = (int(x) for x in arr)
+    h, inter, L, nh, nkv, V, layout, mode, ps, qm, mp, kvbit, kvgroup = (int(x) for x in arr)
     return ModelDesc(h, inter, L, nh, nkv, V, cache_layout=layout, cache_mode=mode, page_size=ps, quant_method=qm,
-                     max_position=mp)
+                     max_position=mp, cache_quant_bit=kvbit, cache_quant_group=kvgroup)
 
 
-@pytest.mark.parametrize("name", ["step_w8a8_paged_l3", "step_fp16_contig_l1_gqa"])
+@pytest.mark.parametrize("name", ["step_w8a8_paged_l3", "step_fp16_contig_l1_gqa", "step_w8a8_fp16kv_paged_l2_gqa"])
 def test_step_golden(name):
     g = np.load(GOLD / f"{name}.npz")
     desc = _desc_from(g["desc"])
@@ -44,7 +44,7 @@ def test_step_golden(name):
         assert tok.tolist() == g[f"s{it}_tokens"].tolist()
         np.testing.assert_allclose(lp, g[f"s{it}_logprobs"], atol=1e-4)
     cache, scale = orc.cache.export()
-    if desc.quant_method == 1:  # integer path end to end: the int8 cache is bit-exact
+    if desc.quant_method == 1 and desc.cache_quant_bit == 8:  # integer path end to end: the int8 cache is bit-exact
         mism = (cache != g["kv_cache_final"]).mean()
         assert mism < 1e-3, f"{mism:.2e} of the int8 KV codes differ"
     assert cache.shape == g["kv_cache_final"].shape and scale.shape == g["kv_scale_final"].shape
