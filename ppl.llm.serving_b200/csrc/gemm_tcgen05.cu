@@ -17,6 +17,7 @@
 // Results are bit-identical to gemm_mma.cu for int8 (integer accumulation, same fp32 epilogue).
 #include <cuda.h>
 
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -560,19 +561,32 @@ struct CfgW4 {
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 8 nibbles (one uint32, element i in bits [4i, 4i+4)) -> 8 fp16 values (q - 8) * scale as 4 packed half2
+// 8 nibbles (one uint32, element i in bits [4i, 4i+4)) -> 8 fp16 values (q - 8) * scale as 4 packed half2.
+// (w >> 4j) & 0x000F000F | 0x64006400 is the half2 (1024 + e_j, 1024 + e_{j+4}) in ONE lop3; the subtraction is exact
+// and the product rounds once: fp16(q * s), what the oracle's dequantisation defines.  Four PRMTs put the pairs back in
+// k order.  19 instructions per 8 elements (the byte-wise version took ~32 and made the converters issue-bound).
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t x, uint32_t m, uint32_t k) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xea;\n" : "=r"(r) : "r"(x), "r"(m), "r"(k));  // (x & m) | k
+    return r;
+}
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 __device__ __forceinline__ uint4 w4_expand8(uint32_t w, __half2 sc) {
     const __half2 bias = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));  // 1032 = 1024 + 8
-    uint32_t o[4];
+    uint32_t p[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t b = (w >> (8 * i)) & 0xFFu;                                   // elements 2i (low nibble), 2i + 1
-        uint32_t pk = (b & 0xFu) | ((b >> 4) << 16) | 0x64006400u;                  // halves 1024 + nibble
+    for (int j = 0; j < 4; ++j) {
+        uint32_t pk = lop3_and_or(w >> (4 * j), 0x000F000Fu, 0x64006400u);           // halves 1024 + e_j, 1024 + e_{j+4}
         __half2 h = *reinterpret_cast<__half2*>(&pk);
-        h = __hmul2(__hsub2(h, bias), sc);                                           // exact q, one rounding: fp16(q * s)
-        o[i] = *reinterpret_cast<uint32_t*>(&h);
+        h = __hmul2(__hsub2(h, bias), sc);
+        p[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    return make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(prmt_b32(p[0], p[1], 0x5410u), prmt_b32(p[2], p[3], 0x5410u),    // (e0, e1) (e2, e3)
+                      prmt_b32(p[0], p[1], 0x7632u), prmt_b32(p[2], p[3], 0x7632u));   // (e4, e5) (e6, e7)
 }
 
 template <int EPI, int MT>
@@ -608,7 +622,7 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(afull_bar(s), 1);
-            mbar_init(bfull_bar(s), 256);
+            mbar_init(bfull_bar(s), 8);   // one elected lane per converter warp
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -691,10 +705,29 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
             const int n_blk = tile / num_m;
             const int kb0 = kb_begin(ks), kb1 = kb_begin(ks + 1);
             const __half* srow = w_scale + (int64_t)(n_blk * W4_BN + r) * gpr;
-            __half sc_next = srow[kb0 >> 1];
+            // scales: one fp16 per 128 elements = per 2 k-blocks, and every thread walks its OWN row (rows are gpr halves
+            // apart), so a per-k-block load is a 32-line-diverged LDG in each of the 8 warps -- ~256 LSU passes per k-block,
+            // most of the 0.24 us an EMPTY k-block cost (round 2 run 28).  Four scales per 8-byte load, the next four in flight.
+            const bool vec = (gpr & 3) == 0 && (reinterpret_cast<uintptr_t>(w_scale) & 7) == 0;
+            auto load4 = [&](int grp) {     // scales [4 grp, 4 grp + 4) of this row as two packed half2
+                if (vec) return __ldg(reinterpret_cast<const uint2*>(srow + 4 * grp));
+                uint32_t h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = 4 * grp + i < gpr ? (uint32_t)__half_as_ushort(srow[4 * grp + i]) : 0u;
+                return make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+            };
+            int grp = kb0 >> 3;
+            uint2 cur = load4(grp), nxt = cur;
+            if (((grp + 1) << 3) < kb1) nxt = load4(grp + 1);
             for (int kb = kb0; kb < kb1; ++kb) {
-                const __half sc1 = sc_next;          // 64-element k-blocks, 128-element groups; next group's scale is
-                if (kb + 1 < kb1) sc_next = srow[(kb + 1) >> 1];  // requested before this block's data arrives
+                if ((kb >> 3) != grp) {
+                    grp = kb >> 3;
+                    cur = nxt;
+                    if (((grp + 1) << 3) < kb1) nxt = load4(grp + 1);
+                }
+                const int j = (kb >> 1) & 3;
+                const uint32_t word = (j & 2) ? cur.y : cur.x;
+                const __half sc1 = __ushort_as_half((unsigned short)((j & 1) ? (word >> 16) : (word & 0xFFFFu)));
                 mbar_wait(afull_bar(stage), phase);
                 const uint32_t sraw = smem_base + stage * C::STAGE_BYTES + C::A_BYTES, sb = sraw + C::RAW_BYTES;
                 const __half2 sc = __halves2half2(sc1, sc1);
@@ -712,7 +745,8 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w) : "memory");
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(bfull_bar(stage));
+                __syncwarp();              // every lane's writes + fence precede the warp's single arrival (256 arrivals
+                if (lane == 0) mbar_arrive(bfull_bar(stage));  // on one mbarrier serialised: 0.24 us per k-block, run 28)
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -748,6 +782,256 @@ __global__ void __launch_bounds__(W4_THREADS, 1)
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- W4A16, transposed: the weight tile goes through TMEM
+// The kernel above keeps BOTH MMA operands in shared memory: per 64-element k-block the tensor core reads 64 KB of it, TMA
+// writes 36 KB and the converters move another 20 KB -- measured (round 2 runs 28-31: temporary skip-a-part switches and
+// clock64 counters per role, profiles/r2_gemm_w4_transposed.txt) the MMAs
+// alone then take 670 cycles per k-block against a floor of 512, the conversion alone 580, together 920: shared-memory
+// bandwidth, not the tensor pipe.  This kernel computes the transposed product instead,
+//     D^T[channel, row] = W[channel, k] . X[row, k]^T        M (MMA) = 128 output channels, N (MMA) = NA activation rows,
+// with the dequantised weight tile as the MMA's A operand IN TENSOR MEMORY (tcgen05.mma [d], [a], b-desc): the
+// converter threads write their 32 fp16 values per k-block straight into their own TMEM lane with tcgen05.st -- no
+// shared-memory round trip, no proxy fence -- and the activations are the (single, N = 256) B operand.  Per k-block the
+// shared memory now sees 32 KB of operand reads, 36 KB of TMA writes and 4 KB of nibble reads.
+// The accumulator holds output channels in lanes: a warp's lanes are 32 consecutive channels of one activation row, so
+// stores (fp16 outputs and the fp32 split-K partials alike) are contiguous per row.
+//   warp 0  TMA producer (activations + packed W)      warps 2-9  converters, then the item's epilogue
+//   warp 1  TMEM alloc + MMA issuer                                 (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4)
+constexpr int W4T_THREADS = 320;
+template <int NA>
+struct CfgW4T {
+    static constexpr int ACT_BYTES = NA * BKB;             // 16 / 32 KB: NA activation rows x 64 fp16
+    static constexpr int RAW_BYTES = W4_BN * (BKB / 4);    // 4 KB
+    static constexpr int STAGE_BYTES = ACT_BYTES + RAW_BYTES;
+    static constexpr int STAGES = NA == 256 ? 6 : 8;
+    static constexpr int A_COLS = BKB / 4;                 // 32 columns: 64 fp16 per lane and k-block
+    static constexpr int TMEM_COLS = 512;                  // NA accumulator columns + STAGES x 32 operand columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static_assert(NA + STAGES * A_COLS <= TMEM_COLS, "tensor memory budget");
+};
+
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <int EPI, int NA>
+__global__ void __launch_bounds__(W4T_THREADS, 1)
+    gemm_w4t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc, int splitk,
+                    float* __restrict__ ws) {
+    using C = CfgW4T<NA>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto xfull_bar = [&](int s) { return bars + 8u * s; };                    // TMA: activations + nibbles landed
+    auto wfull_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };      // converters: weight k-block is in TMEM
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };  // MMAs of the stage retired
+    const uint32_t tfull_bar = bars + 8u * (3 * C::STAGES), tempty_bar = tfull_bar + 8u;
+    const uint32_t tmem_slot = tfull_bar + 16u;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (M + NA - 1) / NA, num_n = N / W4_BN;
+    const int nk = (2 * K) / BKB;   // k-blocks of 64 elements
+    const int gpr = K / 128;        // scale groups per output channel
+    const int num_items = num_m * num_n * splitk;
+    auto kb_begin = [&](int ks) { return (int)((int64_t)nk * ks / splitk); };
+    pdl_trigger();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(xfull_bar(s), 1);
+            mbar_init(wfull_bar(s), 8);   // one elected lane per converter warp
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 8);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_w = tmem_base + NA;   // operand ring: stage s at columns [NA + 32 s, NA + 32 s + 32)
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_x);
+            tma_prefetch_desc(&map_w);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int tile = item / splitk, ks = item - tile * splitk;
+                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                for (int kb = kb_begin(ks); kb < kb_begin(ks + 1); ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sx = smem_base + stage * C::STAGE_BYTES, sraw = sx + C::ACT_BYTES;
+                    mbar_expect_tx(xfull_bar(stage), C::ACT_BYTES + C::RAW_BYTES);
+#pragma unroll
+                    for (int h = 0; h < NA / BM; ++h)   // rows past M read as zero
+                        tma_load_2d(sx + h * BM * BKB, &map_x, xfull_bar(stage), kb * BKB, m_blk * NA + h * BM);
+                    tma_load_2d(sraw, &map_w, xfull_bar(stage), kb * (BKB / 4), n_blk * W4_BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<false>(NA);   // M = 128 channels, N = NA rows
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int ks = item % splitk;
+                const int kb0 = kb_begin(ks), kb1 = kb_begin(ks + 1);
+                mbar_wait(tempty_bar, (uint32_t)(it & 1) ^ 1);   // the previous item's epilogue has drained the accumulator
+                tc_fence_after();
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(xfull_bar(stage), phase);
+                    mbar_wait(wfull_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t dx = make_smem_desc(smem_base + stage * C::STAGE_BYTES);
+                    const uint32_t ta = tmem_w + stage * C::A_COLS;
+#pragma unroll
+                    for (int k = 0; k < BKB / 32; ++k)   // 16 fp16 of K per MMA = 8 operand columns, 32 B of the smem row
+                        tc_mma_ts_f16(tmem_base, ta + 8 * k, dx + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                    tc_commit(empty_bar(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar);
+            }
+        }
+    } else {
+        // thread = output channel r of the tile (its TMEM lane); hf = which 32 of the k-block's 64 elements it converts
+        // and, in the epilogue, which half of the activation rows it stores
+        const int quarter = warp & 3, r = quarter * 32 + lane, hf = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            const int tile = item / splitk, ks = item - tile * splitk;
+            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int kb0 = kb_begin(ks), kb1 = kb_begin(ks + 1);
+            const __half* srow = w_scale + (int64_t)(n_blk * W4_BN + r) * gpr;
+            // one fp16 scale per 128 elements = per 2 k-blocks; four per 8-byte load, the next four in flight
+            const bool vec = (gpr & 3) == 0 && (reinterpret_cast<uintptr_t>(w_scale) & 7) == 0;
+            auto load4 = [&](int grp) {
+                if (vec) return __ldg(reinterpret_cast<const uint2*>(srow + 4 * grp));
+                uint32_t h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = 4 * grp + i < gpr ? (uint32_t)__half_as_ushort(srow[4 * grp + i]) : 0u;
+                return make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+            };
+            int grp = kb0 >> 3;
+            uint2 cur = load4(grp), nxt = cur;
+            if (((grp + 1) << 3) < kb1) nxt = load4(grp + 1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if ((kb >> 3) != grp) {
+                    grp = kb >> 3;
+                    cur = nxt;
+                    if (((grp + 1) << 3) < kb1) nxt = load4(grp + 1);
+                }
+                const int j = (kb >> 1) & 3;
+                const uint32_t word = (j & 2) ? cur.y : cur.x;
+                const __half sc1 = __ushort_as_half((unsigned short)((j & 1) ? (word >> 16) : (word & 0xFFFFu)));
+                const __half2 sc = __halves2half2(sc1, sc1);
+                mbar_wait(xfull_bar(stage), phase);
+                const uint32_t sraw = smem_base + stage * C::STAGE_BYTES + C::ACT_BYTES;
+                uint4 raw;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                             : "r"(sraw + r * 32 + hf * 16));
+                const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint32_t v[16];   // elements [32 hf, 32 hf + 32) of channel r as 16 half2 (k, k + 1) = 16 operand columns
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 e = w4_expand8(wds[c], sc);
+                    v[4 * c] = e.x; v[4 * c + 1] = e.y; v[4 * c + 2] = e.z; v[4 * c + 3] = e.w;
+                }
+                tmem_st16(tmem_w + lane_addr + stage * C::A_COLS + hf * 16, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(wfull_bar(stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+
+            // ---- epilogue of the item: lanes = channels n, accumulator columns = activation rows
+            mbar_wait(tfull_bar, (uint32_t)(it & 1));
+            tc_fence_after();
+            const int n = n_blk * W4_BN + r;
+            constexpr int HALF = NA / 2;
+#pragma unroll 1
+            for (int c = 0; c < HALF / 32; ++c) {
+                const int col0 = hf * HALF + c * 32;
+                const int m0 = m_blk * NA + col0;
+                if (m0 >= M) break;                         // warp-uniform
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + lane_addr + col0, rr);
+                if (splitk > 1) {                           // this slice's partial sums: 128 B per row and warp
+                    float* dst = ws + ((int64_t)ks * M + m0) * N + n;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        if (m0 + jj < M) dst[(int64_t)jj * N] = __uint_as_float(rr[jj]);
+                } else if constexpr (EPI == EPI_SWIGLU) {   // channels (2i, 2i + 1) = (gate, up) sit in neighbouring lanes
+                    __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n >> 1);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float mine = __uint_as_float(rr[jj]);
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                        if (!(lane & 1) && m0 + jj < M) dst[(int64_t)jj * ldc] = __float2half_rn(silu_mul_f32(mine, other));
+                    }
+                } else {
+                    // rows jj, jj + 1: even lanes take row jj of channels (n, n + 1), odd lanes row jj + 1 of (n - 1, n)
+                    __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n & ~1);
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 2) {
+                        const float v0 = __uint_as_float(rr[jj]), v1 = __uint_as_float(rr[jj + 1]);
+                        const float got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
+                        float a = (lane & 1) ? got : v0, b = (lane & 1) ? v1 : got;   // channels (n & ~1), (n & ~1) + 1
+                        const int row = jj + (lane & 1);
+                        if (m0 + row < M) {
+                            __half2* o2 = reinterpret_cast<__half2*>(dst + (int64_t)row * ldc);
+                            if constexpr (EPI == EPI_RESIDUAL) {
+                                const float2 old = __half22float2(*o2);
+                                a = __fadd_rn(old.x, a);
+                                b = __fadd_rn(old.y, b);
+                            }
+                            *o2 = __floats2half2_rn(a, b);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
         }
     }
 
@@ -930,6 +1214,23 @@ int32_t w4_scratch(cudaStream_t s, size_t floats, W4Scratch* out) {
     return B2LLM_OK;
 }
 
+// packed-weight tensor map: [N, K/2] bytes, box {32 B, 128 rows}, no swizzle
+int32_t w4_weight_map(CUtensorMap* mw, const uint8_t* packed, int N, int K) {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    auto key = std::make_tuple((const void*)packed, (uint64_t)N, (uint64_t)(K / 2), (uint32_t)0xFFFF0004u);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+        *mw = it->second;
+        return B2LLM_OK;
+    }
+    const uint64_t dims[2] = {(uint64_t)(K / 2), (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)(K / 2)};
+    const uint32_t box[2] = {(uint32_t)(BKB / 4), (uint32_t)W4_BN};
+    B2_REQUIRE(tma_encode_bytes(mw, packed, 2, dims, strides, box, false), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(W4) failed");
+    g_map_cache[key] = *mw;
+    return B2LLM_OK;
+}
+
 template <int EPI, int MT>
 int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __half* scale, int64_t M, int N, int K, void* out,
                   int64_t ldc) {
@@ -938,21 +1239,7 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     B2_ENSURE_DYN_SMEM(kern, C::SMEM_BYTES);
     CUtensorMap ma, mw;
     B2_REQUIRE(cached_map(&ma, a, (uint64_t)M, (uint64_t)(2 * K), BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(A) failed");
-    {  // packed weights: [N, K/2] bytes, box {32 B, 128 rows}, no swizzle
-        std::lock_guard<std::mutex> lk(g_map_mutex);
-        auto key = std::make_tuple((const void*)packed, (uint64_t)N, (uint64_t)(K / 2), (uint32_t)0xFFFF0004u);
-        auto it = g_map_cache.find(key);
-        if (it != g_map_cache.end()) {
-            mw = it->second;
-        } else {
-            const uint64_t dims[2] = {(uint64_t)(K / 2), (uint64_t)N};
-            const uint64_t strides[1] = {(uint64_t)(K / 2)};
-            const uint32_t box[2] = {(uint32_t)(BKB / 4), (uint32_t)W4_BN};
-            B2_REQUIRE(tma_encode_bytes(&mw, packed, 2, dims, strides, box, false), B2LLM_ERR_DEVICE,
-                       "cuTensorMapEncodeTiled(W4) failed");
-            g_map_cache[key] = mw;
-        }
-    }
+    if (const int32_t rc = w4_weight_map(&mw, packed, N, K)) return rc;
     const int tiles = (int)((M + MT * BM - 1) / (MT * BM)) * (N / W4_BN);
     const int sms = gemm_sm_budget();
     // split-K when the tiles alone leave most of the machine idle: slices of >= 8 k-blocks, about one work item per SM
@@ -977,6 +1264,46 @@ int32_t launch_w4(cudaStream_t s, const void* a, const uint8_t* packed, const __
     return B2LLM_OK;
 }
 
+// the transposed kernel (weights through TMEM): NA activation rows per tile
+template <int EPI, int NA>
+int32_t launch_w4t(cudaStream_t s, const void* a, const uint8_t* packed, const __half* scale, int64_t M, int N, int K, void* out,
+                   int64_t ldc) {
+    using C = CfgW4T<NA>;
+    auto kern = gemm_w4t_kernel<EPI, NA>;
+    B2_ENSURE_DYN_SMEM(kern, C::SMEM_BYTES);
+    CUtensorMap mx, mw;
+    B2_REQUIRE(cached_map(&mx, a, (uint64_t)M, (uint64_t)(2 * K), BM), B2LLM_ERR_DEVICE, "cuTensorMapEncodeTiled(X) failed");
+    if (const int32_t rc = w4_weight_map(&mw, packed, N, K)) return rc;
+    const int tiles = (int)((M + NA - 1) / NA) * (N / W4_BN);
+    const int sms = gemm_sm_budget();
+    // split-K when the tiles alone leave most of the machine idle: slices of >= 8 k-blocks, about one work item per SM
+    const int nk = (2 * K) / BKB;
+    int splitk = 1;
+    if (tiles * 2 <= sms) splitk = std::max(1, std::min(sms / tiles, nk / 8));
+    W4Scratch sc{};
+    if (splitk > 1) {
+        const int32_t rc = w4_scratch(s, (size_t)splitk * (size_t)M * (size_t)N, &sc);
+        if (rc) return rc;
+    }
+    const int items = tiles * splitk;
+    launch_kernel(kern, dim3(items < sms ? items : sms), dim3(W4T_THREADS), C::SMEM_BYTES, s, mx, mw, scale, (int)M, N, K, out, ldc,
+                  splitk, sc.ws);
+    B2_LAUNCH_CHECK();
+    if (splitk > 1) {
+        const int64_t threads = M * (N / 8);
+        launch_kernel(w4_splitk_reduce_kernel<EPI>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, s, (const float*)sc.ws, splitk,
+                      (int)M, N, out, ldc);
+        B2_LAUNCH_CHECK();
+    }
+    return B2LLM_OK;
+}
+
+template <int EPI>
+int32_t launch_w4t_pick(cudaStream_t s, const void* a, const uint8_t* packed, const __half* scale, int64_t M, int N, int K, void* out,
+                        int64_t ldc) {
+    return M > BM ? launch_w4t<EPI, 256>(s, a, packed, scale, M, N, K, out, ldc) : launch_w4t<EPI, 128>(s, a, packed, scale, M, N, K, out, ldc);
+}
+
 }  // namespace
 
 bool gemm_tc_available() { return tma_available(); }
@@ -991,6 +1318,16 @@ int32_t launch_gemm_w4a16(cudaStream_t s, const void* a_fp16, const uint8_t* pac
     }
     if (M == 0) return B2LLM_OK;
     const __half* sc = (const __half*)scale_fp16;
+    // default: the transposed kernel (weight tile through TMEM).  B2LLM_W4_IMPL=ss keeps the both-operands-in-smem kernel
+    // reachable for A/B measurements.
+    static const bool use_ss = [] { const char* e = getenv("B2LLM_W4_IMPL"); return e && !strcmp(e, "ss"); }();
+    if (!use_ss) {
+        switch (epilogue) {
+            case EPI_F16: return launch_w4t_pick<EPI_F16>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+            case EPI_RESIDUAL: return launch_w4t_pick<EPI_RESIDUAL>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+            default: return launch_w4t_pick<EPI_SWIGLU>(s, a_fp16, packed, sc, M, N, K, out, ldc);
+        }
+    }
     // two A tiles per weight tile halve the conversion work, but only pay once the grid still fills half the machine
     // two A tiles per weight tile (MT = 2) halve the conversion work per flop; split-K refills the machine when that leaves
     // few tiles.  It pays while a work item still runs a long K loop -- measured at M = 256 (round 2 run 17): gate_up

@@ -19,6 +19,9 @@ from ppl_llm_serving_b200.engine import _ptr  # noqa: E402
 lib = capi.load_library()
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 shapes = [("qkv", 1280, 8192, 0), ("o", 8192, 1024, 1), ("gate_up", 7168, 8192, 2), ("down", 8192, 3584, 1)]
+import os  # noqa: E402
+if os.environ.get("SHAPES"):          # e.g. SHAPES=gate_up,down ; FUSED_ONLY=1 skips the two-kernel fallback
+    shapes = [s for s in shapes if s[0] in os.environ["SHAPES"].split(",")]
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, N, K, epi in shapes:
     copies = max(2, int(300e6 // (N * K // 2)) + 1)
@@ -35,7 +38,7 @@ for name, N, K, epi in shapes:
         assert lib.b2llm_op_dequant_w4(sp, _ptr(packs[i % copies]), _ptr(scale), N, K, _ptr(scratch)) == 0
         assert lib.b2llm_op_gemm_f16(sp, _ptr(a), _ptr(scratch), M, N, K, epi, _ptr(out), 0, 0) == 0, lib.b2llm_last_error()
 
-    for label, fn in (("fused", fused), ("dequant+f16", twostep)):
+    for label, fn in ((("fused", fused),) if os.environ.get("FUSED_ONLY") else (("fused", fused), ("dequant+f16", twostep))):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
