@@ -836,11 +836,53 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 32 accumulator columns (= activation rows m0 .. m0 + 31) of this lane's output channel n -> memory.  part != nullptr: fp32
+// split-K partials [M][N] of this slice; else the epilogue.  A warp's lanes are 32 consecutive channels of one row.
+template <int EPI>
+__device__ __forceinline__ void w4t_store32(const uint32_t (&rr)[32], int m0, int n, int lane, int M, int N, void* __restrict__ out,
+                                            int64_t ldc, float* __restrict__ part) {
+    if (part != nullptr) {   // 128 B per row and warp
+        float* dst = part + (int64_t)m0 * N + n;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+            if (m0 + jj < M) dst[(int64_t)jj * N] = __uint_as_float(rr[jj]);
+    } else if constexpr (EPI == EPI_SWIGLU) {   // channels (2i, 2i + 1) = (gate, up) sit in neighbouring lanes
+        __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n >> 1);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            const float mine = __uint_as_float(rr[jj]);
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            if (!(lane & 1) && m0 + jj < M) dst[(int64_t)jj * ldc] = __float2half_rn(silu_mul_f32(mine, other));
+        }
+    } else {
+        // rows jj, jj + 1: even lanes take row jj of channels (n, n + 1), odd lanes row jj + 1 of (n - 1, n)
+        __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n & ~1);
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+            const float v0 = __uint_as_float(rr[jj]), v1 = __uint_as_float(rr[jj + 1]);
+            const float got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
+            float a = (lane & 1) ? got : v0, b = (lane & 1) ? v1 : got;   // channels (n & ~1), (n & ~1) + 1
+            const int row = jj + (lane & 1);
+            if (m0 + row < M) {
+                __half2* o2 = reinterpret_cast<__half2*>(dst + (int64_t)row * ldc);
+                if constexpr (EPI == EPI_RESIDUAL) {
+                    const float2 old = __half22float2(*o2);
+                    a = __fadd_rn(old.x, a);
+                    b = __fadd_rn(old.y, b);
+                }
+                *o2 = __floats2half2_rn(a, b);
+            }
+        }
+    }
+}
 template <int EPI, int NA>
 __global__ void __launch_bounds__(W4T_THREADS, 1)
     gemm_w4t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __half* __restrict__ w_scale, int M, int N, int K, void* __restrict__ out, int64_t ldc, int splitk,
                     float* __restrict__ ws) {
+    // Two k-slices are summed by w4_splitk_reduce_kernel through an fp32 scratch in L2.  Summing them inside the kernel --
+    // clusters of two CTAs, rank 1 handing its 128 KB partial tile to rank 0 through distributed shared memory -- was built
+    // and measured (round 2 run 33): gate_up 34.1 -> 47.4 us, down 22.8 -> 42.6 us.  DSMEM moves ~21 B/clk per SM; L2 is faster.
     using C = CfgW4T<NA>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -995,39 +1037,7 @@ __global__ void __launch_bounds__(W4T_THREADS, 1)
                 if (m0 >= M) break;                         // warp-uniform
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + lane_addr + col0, rr);
-                if (splitk > 1) {                           // this slice's partial sums: 128 B per row and warp
-                    float* dst = ws + ((int64_t)ks * M + m0) * N + n;
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj)
-                        if (m0 + jj < M) dst[(int64_t)jj * N] = __uint_as_float(rr[jj]);
-                } else if constexpr (EPI == EPI_SWIGLU) {   // channels (2i, 2i + 1) = (gate, up) sit in neighbouring lanes
-                    __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n >> 1);
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const float mine = __uint_as_float(rr[jj]);
-                        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                        if (!(lane & 1) && m0 + jj < M) dst[(int64_t)jj * ldc] = __float2half_rn(silu_mul_f32(mine, other));
-                    }
-                } else {
-                    // rows jj, jj + 1: even lanes take row jj of channels (n, n + 1), odd lanes row jj + 1 of (n - 1, n)
-                    __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n & ~1);
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj += 2) {
-                        const float v0 = __uint_as_float(rr[jj]), v1 = __uint_as_float(rr[jj + 1]);
-                        const float got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
-                        float a = (lane & 1) ? got : v0, b = (lane & 1) ? v1 : got;   // channels (n & ~1), (n & ~1) + 1
-                        const int row = jj + (lane & 1);
-                        if (m0 + row < M) {
-                            __half2* o2 = reinterpret_cast<__half2*>(dst + (int64_t)row * ldc);
-                            if constexpr (EPI == EPI_RESIDUAL) {
-                                const float2 old = __half22float2(*o2);
-                                a = __fadd_rn(old.x, a);
-                                b = __fadd_rn(old.y, b);
-                            }
-                            *o2 = __floats2half2_rn(a, b);
-                        }
-                    }
-                }
+                w4t_store32<EPI>(rr, m0, n, lane, M, N, out, ldc, splitk > 1 ? ws + (int64_t)ks * M * N : nullptr);
             }
             tc_fence_before();
             __syncwarp();
@@ -1280,12 +1290,12 @@ int32_t launch_w4t(cudaStream_t s, const void* a, const uint8_t* packed, const _
     const int nk = (2 * K) / BKB;
     int splitk = 1;
     if (tiles * 2 <= sms) splitk = std::max(1, std::min(sms / tiles, nk / 8));
+    const int items = tiles * splitk;
     W4Scratch sc{};
     if (splitk > 1) {
         const int32_t rc = w4_scratch(s, (size_t)splitk * (size_t)M * (size_t)N, &sc);
         if (rc) return rc;
     }
-    const int items = tiles * splitk;
     launch_kernel(kern, dim3(items < sms ? items : sms), dim3(W4T_THREADS), C::SMEM_BYTES, s, mx, mw, scale, (int)M, N, K, out, ldc,
                   splitk, sc.ws);
     B2_LAUNCH_CHECK();

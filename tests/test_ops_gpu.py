@@ -90,8 +90,10 @@ def test_w4a16_weight_quant_bit_exact(lib):
 
 # (256, 1280, 8192): one A tile per weight tile + 7 k-slices; (129, 384, 1024): 2 slices with a partial M tile;
 # (256, 3584, 8192): two A tiles per weight tile + 5 k-slices of 25 k-blocks (the gate_up / down plan of 70B at TP = 8, half the N)
+# two k-slices summed inside the kernel by clusters of two CTAs (50 .. 74 tiles): (200, 8192, 3584) = the down projection of
+# 70B at TP = 8 with a ragged M, (256, 7168, 1024) = gate_up's width, (100, 8192, 1024) the same with the 128-row tile
 @pytest.mark.parametrize("M,N,K", [(1, 128, 128), (100, 256, 512), (256, 1280, 8192), (129, 384, 1024), (300, 512, 256),
-                                   (256, 3584, 8192)])
+                                   (256, 3584, 8192), (200, 8192, 3584), (256, 7168, 1024), (100, 8192, 1024), (64, 256, 256)])
 def test_gemm_w4a16_fused(lib, M, N, K):
     """fused W4A16 tcgen05 GEMM (nibbles expanded to fp16(q * scale) by converter warps inside the kernel) against
     the oracle's definition; the operand values are bit-identical, only the fp32 accumulation order differs"""
