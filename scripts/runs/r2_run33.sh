@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: B2LLM_W4_PAIR selected an in-kernel two-slice reduction that was measured here, found slower and removed again
+# (profiles/r2_gemm_w4_transposed.txt section 5).
 # run 33: transposed W4A16 kernel with the in-kernel two-slice reduction (clusters of two, DSMEM): correctness, then timing
 # with and without it (B2LLM_W4_PAIR=0 -> fp32 scratch + reduce kernel)
 mkdir -p gpurun_out
