@@ -846,35 +846,48 @@ __device__ __forceinline__ void w4t_store32(const uint32_t (&rr)[32], int m0, in
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
             if (m0 + jj < M) dst[(int64_t)jj * N] = __uint_as_float(rr[jj]);
-    } else if constexpr (EPI == EPI_SWIGLU) {   // channels (2i, 2i + 1) = (gate, up) sit in neighbouring lanes
-        __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n >> 1);
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const float mine = __uint_as_float(rr[jj]);
-            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            if (!(lane & 1) && m0 + jj < M) dst[(int64_t)jj * ldc] = __float2half_rn(silu_mul_f32(mine, other));
-        }
     } else {
-        // rows jj, jj + 1: even lanes take row jj of channels (n, n + 1), odd lanes row jj + 1 of (n - 1, n)
-        __half* dst = reinterpret_cast<__half*>(out) + (int64_t)m0 * ldc + (n & ~1);
+        // Lane pairs exchange so that every lane owns ONE row of a channel pair: even lanes row jj of channels (n, n + 1),
+        // odd lanes row jj + 1 of (n - 1, n).  Three passes (exchange, loads, math + stores): a load placed after a store to
+        // the same array cannot be hoisted by the compiler, and 64 dependent read-modify-writes cost 45K cycles per tile
+        // (round 2 run 35); the SwiGLU chain (shuffle -> expf -> store) likewise ran one column at a time.
+        const int odd = lane & 1;
+        float a[16], b[16];   // values of channels (n & ~1) and (n & ~1) + 1 in this lane's row of each row pair
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 2) {
-            const float v0 = __uint_as_float(rr[jj]), v1 = __uint_as_float(rr[jj + 1]);
-            const float got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
-            float a = (lane & 1) ? got : v0, b = (lane & 1) ? v1 : got;   // channels (n & ~1), (n & ~1) + 1
-            const int row = jj + (lane & 1);
-            if (m0 + row < M) {
-                __half2* o2 = reinterpret_cast<__half2*>(dst + (int64_t)row * ldc);
-                if constexpr (EPI == EPI_RESIDUAL) {
-                    const float2 old = __half22float2(*o2);
-                    a = __fadd_rn(old.x, a);
-                    b = __fadd_rn(old.y, b);
+        for (int p = 0; p < 16; ++p) {
+            const float v0 = __uint_as_float(rr[2 * p]), v1 = __uint_as_float(rr[2 * p + 1]);
+            const float got = __shfl_xor_sync(0xffffffffu, odd ? v0 : v1, 1);
+            a[p] = odd ? got : v0;
+            b[p] = odd ? v1 : got;
+        }
+        if constexpr (EPI == EPI_SWIGLU) {   // (gate, up) = channels (2i, 2i + 1) -> one output column i
+            __half* dst = reinterpret_cast<__half*>(out) + (int64_t)(m0 + odd) * ldc + (n >> 1);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) a[p] = silu_mul_f32(a[p], b[p]);
+#pragma unroll
+            for (int p = 0; p < 16; ++p)
+                if (m0 + 2 * p + odd < M) dst[(int64_t)(2 * p) * ldc] = __float2half_rn(a[p]);
+        } else {
+            __half2* dst = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out) + (int64_t)(m0 + odd) * ldc + (n & ~1));
+            const int64_t step = ldc;   // two rows, in half2 units
+            if constexpr (EPI == EPI_RESIDUAL) {
+                __half2 old[16];
+#pragma unroll
+                for (int p = 0; p < 16; ++p) old[p] = m0 + 2 * p + odd < M ? dst[(int64_t)p * step] : __half2();
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const float2 o2 = __half22float2(old[p]);
+                    a[p] = __fadd_rn(o2.x, a[p]);
+                    b[p] = __fadd_rn(o2.y, b[p]);
                 }
-                *o2 = __floats2half2_rn(a, b);
             }
+#pragma unroll
+            for (int p = 0; p < 16; ++p)
+                if (m0 + 2 * p + odd < M) dst[(int64_t)p * step] = __floats2half2_rn(a[p], b[p]);
         }
     }
 }
+
 template <int EPI, int NA>
 __global__ void __launch_bounds__(W4T_THREADS, 1)
     gemm_w4t_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -1286,10 +1299,14 @@ int32_t launch_w4t(cudaStream_t s, const void* a, const uint8_t* packed, const _
     if (const int32_t rc = w4_weight_map(&mw, packed, N, K)) return rc;
     const int tiles = (int)((M + NA - 1) / NA) * (N / W4_BN);
     const int sms = gemm_sm_budget();
-    // split-K when the tiles alone leave most of the machine idle: slices of >= 8 k-blocks, about one work item per SM
+    // split-K when the tiles alone leave most of the machine idle: about one work item per SM, slices of >= 16 k-blocks (a
+    // slice costs the fp32 scratch round trip and the reduce kernel: o of 70B at TP = 8, 16 k-blocks, is 14.0 us whole and
+    // 14.6 us in two slices; down, 56 k-blocks, 27.4 vs 22.0 -- round 2 run 36)
     const int nk = (2 * K) / BKB;
     int splitk = 1;
-    if (tiles * 2 <= sms) splitk = std::max(1, std::min(sms / tiles, nk / 8));
+    if (tiles * 2 <= sms) splitk = std::max(1, std::min(sms / tiles, nk / 16));
+    static const int force_split = [] { const char* e = getenv("B2LLM_W4_SPLITK"); return e ? atoi(e) : 0; }();   // experiments
+    if (force_split > 0) splitk = std::max(1, std::min(std::min(force_split, nk), std::max(1, sms / tiles)));
     const int items = tiles * splitk;
     W4Scratch sc{};
     if (splitk > 1) {
