@@ -292,9 +292,10 @@ int32_t launch_attention_prefill_mma(cudaStream_t s, const AttnArgs& a) {
 }
 
 int32_t launch_attention_prefill(cudaStream_t s, const AttnArgs& a, int which) {
-    // the tcgen05 / TMEM kernel is the default since round 2 run 8 (602.7 vs 201.9 TFLOP/s causal at 8 x 4096 tokens,
-    // profiles/r2_prefill_run8.txt); steps with cached prefixes fall back to the mma.sync kernel inside it
-    // (B2LLM_ERR_UNSUPPORTED).  B2LLM_PREFILL_IMPL=mma keeps the mma.sync kernel for everything.
+    // the tcgen05 / TMEM kernel (P as hi + lo fp16 halves) is the default since round 2 run 10: 519.2 vs 201.9 TFLOP/s causal
+    // at 8 x 4096 tokens (profiles/r2_prefill_attention.txt; 602.7 with a single fp16 P, rejected on end-to-end parity);
+    // steps with cached prefixes fall back to the mma.sync kernel inside it (B2LLM_ERR_UNSUPPORTED).
+    // B2LLM_PREFILL_IMPL=mma keeps the mma.sync kernel for everything.
     static const bool env_tc = [] {
         const char* e = getenv("B2LLM_PREFILL_IMPL");
         return !(e != nullptr && e[0] == 'm');
