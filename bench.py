@@ -427,7 +427,7 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
                           "NVLink peer memory = all-reduce of the fp16 partials + residual add + RMSNorm + int8 quant (ncclAllReduce + "
                           "separate kernels with B2LLM_TP_JOIN=nccl); + one ncclAllGather(fp32) of the vocab-parallel logits per step",
            "parity_gate": [], "runs": []}
-    quants = [1] + ([2] if world == 8 else [])
+    quants = [1, 2]   # W8A8 and W4A16 (the latter is timed at N = 8 only, but its kernel is gated at every N)
     for q in quants:
         try:
             out["parity_gate"].append(tp_parity_gate(torch, dist, world, rank, local_rank, comm, q))
