@@ -441,6 +441,9 @@ def tp_leg(args, torch, dist, world, rank, local_rank, hbm_peak):
     if world == 4:
         shapes.append(("LLaMA-2-13B W8A8", LLAMA2_13B, 1, 512, 4096,
                        "BASELINE configs[2]: B=512 at the largest kv_len <= 4096 the reference's KV budget fits (literal needs 268 GB/GPU)"))
+    if args.tp_filter:
+        shapes = [sh for sh in shapes if args.tp_filter in sh[0]]
+        out["shape_filter"] = args.tp_filter
     for name, dims, quant, batch, kv_target, note in shapes:
         cfg = ModelConfig(**dims, page_size=PAGE, max_position=max(4096, kv_target + 16), quant_method=quant)
         if args.layers != 32:
@@ -517,6 +520,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tp", action="store_true", help="N > 1: skip the tensor-parallel leg")
     ap.add_argument("--no-alt", action="store_true", help="N = 1: skip the config-2b alternative shape")
+    ap.add_argument("--tp-filter", default="", help="N > 1: time only the tensor-parallel shapes whose model name contains this "
+                                                    "(e.g. 70B); the replica leg and the parity gates still run")
     ap.add_argument("--kv-budget-tokens", type=int, default=0,
                     help="allocate exactly this many KV tokens instead of the reference's 0.94 x free-memory budget "
                          "(profiling runs: ncu saves / restores all device memory on every replay pass)")
