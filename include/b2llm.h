@@ -281,6 +281,12 @@ B2LLM_API int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_head
  * ENGINE_CONF_DECODING_ATTN_SPLIT_K = 1 "heuristic" and ENGINE_CONF_DECODING_ATTN_TPB knobs (resource_manager.cc:74-106) */
 B2LLM_API int32_t b2llm_attention_decode_plan(int64_t decoding_batches, int32_t num_heads, int32_t num_kv_heads,
                                               int64_t max_kv_len, int32_t* nsplit, int32_t* warps);
+/* Debug aid: per-CTA timeline of the decode attention kernel.  While a device buffer of 4 x capacity_ctas uint64 is armed,
+ * every launch of the kernel with at most capacity_ctas CTAs writes {start ns, main loop entered ns, end ns, SM id}
+ * (%globaltimer / %smid) at [4 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))]; later launches
+ * overwrite earlier ones.  device_buf = NULL disarms.  Process-wide, not thread-safe against concurrent launches;
+ * no reference counterpart. */
+B2LLM_API int32_t b2llm_debug_attention_trace(void* device_buf, int64_t capacity_ctas);
 B2LLM_API int32_t b2llm_op_attention(void* stream, const void* qkv_fp16, const b2llm_step* step, int32_t num_heads,
                                      const b2llm_kv_geom* geom, int32_t layer, const void* kv_cache,
                                      const void* kv_scale, void* workspace, void* out_fp16, int32_t impl);

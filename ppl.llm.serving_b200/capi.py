@@ -70,6 +70,7 @@ SIGNATURES = {
     "b2llm_engine_last_launch_count": (_I64, [_P]),
     "b2llm_engine_tp_join_stats": (_I32, [_P, C.POINTER(C.c_double)]),
     "b2llm_attention_decode_plan": (_I32, [_I64, _I32, _I32, _I64, C.POINTER(_I32), C.POINTER(_I32)]),
+    "b2llm_debug_attention_trace": (_I32, [C.c_void_p, _I64]),
     "b2llm_engine_profile": (_I32, [_P, _I32]),
     "b2llm_engine_profile_read": (_I32, [_P, C.POINTER(C.c_double), C.POINTER(_I64), _I32]),
     "b2llm_engine_debug_read": (_I32, [_P, _I32, _P, _U64]),

@@ -24,6 +24,7 @@
 //    MMA kernel (impl = 1).
 //
 // Numeric contract: oracle/llama_ref.py attention_decode / _attend.
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -54,6 +55,7 @@ struct AttnParams {
     float* ws;             // split partials
     int nsplit;
     int64_t token_begin, token_end;
+    unsigned long long* trace;  // debug (b2llm_debug_attention_trace): 4 words per CTA of the decode kernel, else nullptr
 };
 
 // ------------------------------------------------------------------------------------------
@@ -376,6 +378,25 @@ __device__ __forceinline__ int acc_dim(int i, int g, int hi) {
 // (cache layouts 2 and 3, where k / v is an outer dimension; the smem image is unchanged: K | V | K scales | V scales).
 // KV16: fp16 cache without scales (cache_quant_bit 0): 8 KB stages of four 128 B-swizzled tiles, ldmatrix operands
 // (process_unit16); same ring, walk, softmax, split and merge code.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// per-CTA timeline of the decode kernel (debug aid, off unless b2llm_debug_attention_trace armed it):
+// {start ns, main loop entered ns, end ns, SM id} at trace[4 * linear CTA id]
+__device__ __forceinline__ void trace_cta(unsigned long long* trace, unsigned long long t0, unsigned long long t1) {
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* w = trace + 4ull * (blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z));
+        w[0] = t0;
+        w[1] = t1;
+        w[2] = global_timer_ns();
+        w[3] = smid;
+    }
+}
+
 template <int G, int WARPS, int LOADER, bool KV16>
 __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
@@ -383,6 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     constexpr bool TMA = LOADER != 0, SLIM = LOADER >= 2, MERGED = LOADER == 3;
     constexpr int STG = KV16 ? STAGE16 : STAGE;  // bytes per ring stage
     extern __shared__ uint8_t smem_raw[];
+    const unsigned long long tr0 = p.trace ? global_timer_ns() : 0ull;
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -602,6 +624,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
     }
     int stg = 0;
     uint32_t phase = 0;
+    const unsigned long long tr1 = p.trace ? global_timer_ns() : 0ull;
     for (int u = u0 + warp; u < u1; u += WARPS) {
         if constexpr (TMA) {
             mbar_wait(wbar + 8u * stg, phase);
@@ -698,6 +721,7 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
                 }
             }
         }
+        trace_cta(p.trace, tr0, tr1);
         return;
     }
     __syncthreads();  // all rings are dead from here on
@@ -744,9 +768,13 @@ __global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
             }
         }
     }
+    trace_cta(p.trace, tr0, tr1);
 }
 
-// merge split partials: one warp per (sequence, q head)
+// merge split partials: one warp per (sequence, q head).  The per-split maxima / sums are read lane-parallel (one split per
+// lane) and the partial rows by an unrolled loop of 8-byte loads, so the loads of many splits are in flight at once: the
+// first version walked the splits in two scalar loops, a chain of ~2 x nsplit memory latencies that made the merge ~20 us of
+// a 137 us launch at 13 splits (round 2 run 41).  Both sums still run in ascending split order: bit-identical results.
 __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict__ ws, int nq, int nsplit, int64_t rows,
                                                         __half* __restrict__ out) {
     pdl_trigger();
@@ -756,18 +784,34 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict
     if (w >= rows) return;
     const float* base = ws + w * nsplit * 130;
     float mm = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, base[s * 130 + 128]);
+    for (int s = lane; s < nsplit; s += 32) mm = fmaxf(mm, __ldcg(base + s * 130 + 128));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
     const float ms = mm == -INFINITY ? 0.f : mm;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, ll = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float f = exp2f(base[s * 130 + 128] - ms);
-        ll += base[s * 130 + 129] * f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] += base[s * 130 + lane * 4 + i] * f;
+    for (int s0 = 0; s0 < nsplit; s0 += 32) {
+        float f_l = 0.f, l_l = 0.f;   // lane j: rescaling factor and row sum of split s0 + j
+        if (s0 + lane < nsplit) {
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + (s0 + lane) * 130 + 128));
+            f_l = exp2f(ml.x - ms);
+            l_l = ml.y;
+        }
+        const int cnt = min(32, nsplit - s0);
+#pragma unroll 8
+        for (int j = 0; j < cnt; ++j) {
+            const float f = __shfl_sync(0xffffffffu, f_l, j);
+            ll += __shfl_sync(0xffffffffu, l_l, j) * f;   // same fused multiply-add, same order as the scalar loop it replaces
+            const float2* row = reinterpret_cast<const float2*>(base + (s0 + j) * 130 + lane * 4);   // 520-byte rows: 8-byte aligned
+            const float2 a = __ldcg(row), b = __ldcg(row + 1);
+            acc[0] += a.x * f;
+            acc[1] += a.y * f;
+            acc[2] += b.x * f;
+            acc[3] += b.y * f;
+        }
     }
     // w = b * nq + hq and decode token index == b
-#pragma unroll
-    for (int i = 0; i < 4; ++i) out[w * 128 + lane * 4 + i] = __float2half_rn(acc[i] / ll);
+    const __half2 h0 = __floats2half2_rn(acc[0] / ll, acc[1] / ll), h1 = __floats2half2_rn(acc[2] / ll, acc[3] / ll);
+    *reinterpret_cast<uint2*>(out + w * 128 + lane * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
 }
 
 // How many KV splits and how many warps per CTA.  The kernel's unit of residency is a warp (12 warp slots per SM,
@@ -991,6 +1035,10 @@ int32_t launch_attention_simple(cudaStream_t s, const AttnArgs& a, int64_t token
     return B2LLM_OK;
 }
 
+// debug: device buffer armed by b2llm_debug_attention_trace (4 x uint64 per CTA), nullptr = off
+std::atomic<unsigned long long*> g_attn_trace{nullptr};
+std::atomic<long long> g_attn_trace_ctas{0};
+
 template <int G, int WARPS, int LOADER, bool KV16 = false>
 static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, const DecodeTma& tc) {
     auto kern = attn_decode_kernel<G, WARPS, LOADER, KV16>;
@@ -1001,6 +1049,8 @@ static int32_t launch_decode(cudaStream_t s, AttnParams& p, const KvMaps& maps, 
     const int gq = p.nq / p.nkv;
     const int chunks = (gq + G - 1) / G;
     dim3 grid(p.nsplit, p.nkv * chunks, p.decoding_batches);
+    unsigned long long* tr = g_attn_trace.load();
+    p.trace = tr != nullptr && (long long)grid.x * grid.y * grid.z <= g_attn_trace_ctas.load() ? tr : nullptr;
     launch_kernel(kern, grid, dim3(WARPS * 32), smem_bytes, s, p, maps.kv, maps.sc, tc);
     B2_LAUNCH_CHECK();
     if (p.nsplit > 1) {
@@ -1108,3 +1158,9 @@ int32_t launch_attention_decode_mma(cudaStream_t s, const AttnArgs& a) {
 }
 
 }  // namespace b2llm
+
+extern "C" int32_t b2llm_debug_attention_trace(void* device_buf, int64_t capacity_ctas) {
+    b2llm::g_attn_trace_ctas.store(device_buf != nullptr ? (long long)capacity_ctas : 0);
+    b2llm::g_attn_trace.store(reinterpret_cast<unsigned long long*>(device_buf));
+    return B2LLM_OK;
+}
