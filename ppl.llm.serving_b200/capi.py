@@ -11,7 +11,8 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libb2llm.so"
+# B2LLM_LIB: another build of the same library (A/B measurements of kernel variants); default = the in-tree build
+LIB_PATH = Path(os.environ["B2LLM_LIB"]).resolve() if os.environ.get("B2LLM_LIB") else _HERE / "lib" / "libb2llm.so"
 
 B2LLM_OK = 0
 QUANT_NONE, QUANT_ONLINE_I8I8, QUANT_W4A16 = 0, 1, 2

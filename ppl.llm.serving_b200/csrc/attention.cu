@@ -141,7 +141,13 @@ __global__ void __launch_bounds__(128) attn_simple_kernel(AttnParams p) {
 // ------------------------------------------------------------------------------------------
 // tensor-core split-KV decode kernel (D = 128, int8 group-8 cache)
 constexpr int UNIT = 16;                 // tokens per warp iteration
-constexpr int NSTAGE = 3;
+#ifndef B2_ATTN_NSTAGE
+#define B2_ATTN_NSTAGE 3
+#endif
+// 4 stages (3 units in flight, but only 10 one-warp CTAs per SM) were measured against 3 x 12 (round 2 run 43): the headline
+// shape slows from 0.7745 to 0.7990 ms per launch, 13B / TP 4 from 0.650 to 0.719; resident warps beat deeper rings.
+constexpr int NSTAGE = B2_ATTN_NSTAGE;            // ring stages per warp: NSTAGE - 1 units in flight while one is consumed
+constexpr int kCtasPerSm = NSTAGE >= 4 ? 10 : 12; // one-warp CTAs per SM the ring leaves room for (int8 cache: 5 KB per stage)
 constexpr int K_BYTES = UNIT * 128;      // 2048
 constexpr int S_BYTES = UNIT * 32;       // 512 (16 fp16 scales per token)
 constexpr int STAGE = 2 * K_BYTES + 2 * S_BYTES;  // 5120: K | V | K scales | V scales
@@ -398,7 +404,7 @@ __device__ __forceinline__ void trace_cta(unsigned long long* trace, unsigned lo
 }
 
 template <int G, int WARPS, int LOADER, bool KV16>
-__global__ void __launch_bounds__(WARPS * 32, 12 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, kCtasPerSm / WARPS)
     attn_decode_kernel(AttnParams p, const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_sc,
                        DecodeTma tc) {
     constexpr bool TMA = LOADER != 0, SLIM = LOADER >= 2, MERGED = LOADER == 3;
@@ -823,7 +829,7 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict
 struct DecodePlan {
     int nsplit, warps;
 };
-constexpr int64_t kWarpSlots = 148 * 12;
+constexpr int64_t kWarpSlots = 148 * kCtasPerSm;
 
 int64_t attention_workspace_rows(int64_t batch) { return std::max<int64_t>(2 * batch + 444, 4096); }
 
