@@ -277,7 +277,8 @@ B2LLM_API int32_t b2llm_op_rope_kv_append(void* stream, void* qkv_fp16, const b2
  * the step has cached prefixes), 8 mma.sync */
 B2LLM_API int64_t b2llm_attention_workspace_size(int64_t batch, int32_t num_heads, int32_t head_dim);
 /* the decode attention kernel's launch plan (host logic only, needs no device): KV splits per sequence and warps per CTA
- * for `decoding_batches` sequences of at most `max_kv_len` cached tokens -- the counterpart of the reference's
+ * for `decoding_batches` sequences of at most `max_kv_len` cached tokens (one wave of one-warp CTAs where a cut into
+ * 0.75 .. 1.0 of the 148 x 12 warp slots exists, else the cut with the best-filled last wave) -- the counterpart of the reference's
  * ENGINE_CONF_DECODING_ATTN_SPLIT_K = 1 "heuristic" and ENGINE_CONF_DECODING_ATTN_TPB knobs (resource_manager.cc:74-106) */
 B2LLM_API int32_t b2llm_attention_decode_plan(int64_t decoding_batches, int32_t num_heads, int32_t num_kv_heads,
                                               int64_t max_kv_len, int32_t* nsplit, int32_t* warps);

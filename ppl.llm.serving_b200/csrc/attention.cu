@@ -842,6 +842,17 @@ DecodePlan plan_decode(int64_t base_ctas, int64_t batch, int64_t max_kv_len) {
     DecodePlan best{1, 1};
     double best_eff = eff(1, 1);
     if (best_eff >= 0.90) return best;
+    // ONE wave when the sequences can be cut into between 0.75 and 1.0 of the warp slots: every CTA starts at once and they
+    // finish together -- no second-wave ramp, no staggered drain, the fewest partials to merge.  ~1500 one-warp CTAs already
+    // saturate HBM (per-CTA timelines, profiles/r2_attention_cta_timeline_run41.txt), so the idle slots cost nothing.  Measured
+    // at the 70B / TP 8 per-rank shape (256 base CTAs, kv 8192; round 2 run 45): 6 splits = 0.86 of one wave 0.125 ms per
+    // launch; 13 splits = 0.94 of two waves (what the efficiency search below picks) 0.144 ms; 5 / 4 splits 0.142 / 0.140 ms.
+    if (base_ctas < kWarpSlots) {
+        int64_t nw = kWarpSlots / base_ctas;                              // the finest cut that still fits one wave
+        nw = std::min(nw, units / 8);                                      // at least 8 units per warp
+        nw = std::min(nw, attention_workspace_rows(batch) / std::max<int64_t>(1, batch));   // one-warp CTAs: splits = nw
+        if (nw >= 2 && (double)(base_ctas * nw) >= 0.75 * (double)kWarpSlots) return DecodePlan{(int)nw, 1};
+    }
     for (int64_t nw = 2; nw <= 64; ++nw) {       // total ways a sequence's KV range is cut (splits x warps)
         if (units / nw < 8) break;
         for (int w : {4, 2, 1}) {                // prefer warps of one CTA (merged in shared memory) over splits

@@ -77,8 +77,9 @@ def test_incremental_walk_contiguous_index_mode(warps):
 def test_decode_plan_wave_efficiency():
     """host logic of the decode attention launch (csrc/attention.cu plan_decode), through the C ABI without a device: the
     kernel's unit of residency is a warp (148 SMs x 12 slots = 1776); a plan is (KV splits, warps per CTA).  Properties:
-    big grids are left alone; shapes that would run in a poorly filled last wave get split until the wave efficiency is
-    >= 0.9 where the sequence length allows; at least 8 units (128 tokens) per warp; partials fit the workspace."""
+    big grids are left alone; shapes that fit ONE wave at 0.75 .. 1.0 of the slots take that cut (one-warp CTAs); other shapes
+    that would run in a poorly filled last wave get split until the wave efficiency is >= 0.9 where the sequence length
+    allows; at least 8 units (128 tokens) per warp; partials fit the workspace."""
     import ctypes as C
     import b200_import
     b200_import.load()
@@ -102,9 +103,14 @@ def test_decode_plan_wave_efficiency():
     assert plan(1024, 16, 16, 512) == (1, 1)                      # TP = 2: 9.2 waves
     e, n, w = eff(1024, 4, 4, 512)                                # 7B TP = 8: 2.3 waves alone (0.77)
     assert e >= 0.9 and n * w > 1
-    e, n, w = eff(256, 8, 1, 8192)                                # 70B TP = 8: 256 CTAs
-    assert e >= 0.9 and 8192 // 16 // (n * w) >= 8
+    e, n, w = eff(256, 8, 1, 8192)                                # 70B TP = 8: 256 CTAs -> ONE wave, 1536 of 1776 slots
+    assert (n, w) == (6, 1) and abs(e - 1536 / 1776) < 1e-9       # measured faster than 13 splits = 0.94 of two waves (run 45)
+    assert 8192 // 16 // (n * w) >= 8
     assert 256 * n <= max(2 * 256 + 444, 4096)                    # split partials fit attention_workspace_rows
+    assert plan(16, 32, 32, 4096) == (3, 1)                       # 512 base CTAs -> 1536 in one wave
+    assert plan(16, 32, 32, 300) == (1, 2)                        # 19 units allow 2 cuts: 1024 CTAs < 0.75 of a wave -> the old search (two warps)
+    e, n, w = eff(512, 10, 10, 2640)                              # 13B TP = 4: 2.9 waves, no single-wave cut -> efficiency search
+    assert e >= 0.9
     for batch, nq, nkv, kv in [(1, 32, 32, 17), (3, 8, 2, 300), (48, 4, 4, 400), (7, 64, 8, 4096), (2000, 40, 40, 33)]:
         n, w = plan(batch, nq, nkv, kv)
         assert n >= 1 and w in (1, 2, 4)
