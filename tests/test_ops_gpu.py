@@ -93,7 +93,10 @@ def test_w4a16_weight_quant_bit_exact(lib):
 # two k-slices summed inside the kernel by clusters of two CTAs (50 .. 74 tiles): (200, 8192, 3584) = the down projection of
 # 70B at TP = 8 with a ragged M, (256, 7168, 1024) = gate_up's width, (100, 8192, 1024) the same with the 128-row tile
 @pytest.mark.parametrize("M,N,K", [(1, 128, 128), (100, 256, 512), (256, 1280, 8192), (129, 384, 1024), (300, 512, 256),
-                                   (256, 3584, 8192), (200, 8192, 3584), (256, 7168, 1024), (100, 8192, 1024), (64, 256, 256)])
+                                   (256, 3584, 8192), (200, 8192, 3584), (256, 7168, 1024), (100, 8192, 1024), (64, 256, 256),
+                                   # more work items than SMs: CTAs run a second item over the same accumulator (160 tiles of the
+                                   # 128-row tile; 2 row blocks x 100 = 200 tiles of the 256-row tile)
+                                   (64, 20480, 256), (300, 12800, 256)])
 def test_gemm_w4a16_fused(lib, M, N, K):
     """fused W4A16 tcgen05 GEMM (nibbles expanded to fp16(q * scale) by converter warps inside the kernel) against
     the oracle's definition; the operand values are bit-identical, only the fp32 accumulation order differs"""
